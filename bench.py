@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- ALS iterations/s on the BASELINE.json headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config NAME]
+
+One "step" = one ALS iteration (Gramian + X<-Y, Gramian + Y<-X; AlternatingLeastSquares.java
+:227-229) over the synthetic workload of SURVEY.md 8(d), generated on the device.
+Prints ONE JSON line (rank 0).  `value` is iterations/s with everything resident in HBM;
+`e2e` is the same metric through the C ABI with HOST buffers (CSR + Y0 uploaded from pinned
+memory, K iterations, X and Y read back) -- the number to compare with the reference arm.
+`--impl reference` times the CPU oracle (the C port of the reference's Java ALS; there is no
+JVM in this image) on all host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 1234567890  # RandomManager test seed (common/.../random/RandomManager.java:52)
+
+# BASELINE.json configs: name -> users, items, nnz/user, k
+CONFIGS = {
+    "c1": dict(users=10_000, items=2_000, nnz_per_user=20, k=16),
+    "c2": dict(users=1_000_000, items=100_000, nnz_per_user=50, k=32),
+    "c3": dict(users=10_000_000, items=1_000_000, nnz_per_user=100, k=64),
+}
+WORKLOAD_NAMES = {
+    "c1": "10k x 2k, 20 nnz/user, k=16",
+    "c2": "1M x 100k, 50 nnz/user, k=32",
+    "c3": "10M x 1M, 100 nnz/user, k=64 (headline)",
+}
+
+
+def algorithmic_bytes(U, I, nnz, k):
+    """B_iter = 2*NNZ*(4k+8) + 2*(U+I)*4k + 2*(U+I+2)*8."""
+    return 2 * nnz * (4 * k + 8) + 2 * (U + I) * 4 * k + 2 * (U + I + 2) * 8
+
+
+def update_launch_bytes(rows, nnz, k):
+    """Algorithmic bytes of ONE row-update launch: per entry one 4k-byte factor row + 4 B index
+    + 4 B value; per row one 4k-byte write and one 8-byte row pointer; the k x k fp64 Gramian."""
+    return nnz * (4 * k + 8) + rows * 4 * k + (rows + 1) * 8 + k * k * 8
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6),
+                                  ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU baseline: the oracle (C port of the reference's Java ALS) on a bounded sample.
+def cpu_baseline_from_sample(cfg, user_rows, item_rows, Y, X, budget_note):
+    """user_rows/item_rows: (ptr, idx, val) CSR slices; Y, X: full opposite factors (host).
+    Times one X-half over the user sample and one Y-half over the item sample with all host
+    threads (100-row work units, AlternatingLeastSquares.java:77), plus the single-threaded
+    transposeTimesSelf (MatrixUtils.java:219-239) on a row sample, and scales each linearly
+    to the full workload."""
+    from oracle import oracle as O
+    U, I, k = cfg["users"], cfg["items"], cfg["k"]
+    cores = os.cpu_count() or 1
+    nu, ni = user_rows[0].size - 1, item_rows[0].size - 1
+    g_rows = min(I, 200_000)
+    t0 = time.perf_counter()
+    G = O.transpose_times_self(Y[:g_rows])
+    t_g = (time.perf_counter() - t0) / g_rows
+    out = np.zeros((nu, k), np.float32)
+    t0 = time.perf_counter()
+    O.als_half(user_rows[0], user_rows[1], user_rows[2], Y, G, out, n_threads=cores)
+    t_x = (time.perf_counter() - t0) / max(nu, 1)
+    G = O.transpose_times_self(X[:g_rows])
+    out = np.zeros((ni, k), np.float32)
+    t0 = time.perf_counter()
+    O.als_half(item_rows[0], item_rows[1], item_rows[2], X, G, out, n_threads=cores)
+    t_y = (time.perf_counter() - t0) / max(ni, 1)
+    t_iter = t_x * U + t_y * I + t_g * (U + I)
+    return {
+        "value": 1.0 / t_iter, "unit": "iterations/s", "cores": cores, "kind": "port",
+        "sample": ("C port of the reference Java ALS (oracle/als_oracle.c; no JVM on the box): "
+                   "X-half on %d of %d users + Y-half on %d of %d items with %d threads, "
+                   "single-threaded Gramian on %d rows, each scaled linearly to the full "
+                   "workload; %s" % (nu, U, ni, I, cores, g_rows, budget_note)),
+        "seconds_per_iteration_extrapolated": t_iter,
+        "split_s": {"x_half": t_x * U, "y_half": t_y * I, "gramians": t_g * (U + I)},
+    }
+
+
+def sample_sizes(cfg, scale=1.0):
+    # ~10-30 s of CPU work: cost/row ~ nnz*k^2 (fp64 rank-1) + ~2.7*k^3 (Householder QR)
+    k, nnz = cfg["k"], cfg["nnz_per_user"]
+    per_user = nnz * k * k + 2.7 * k ** 3
+    per_item = nnz * cfg["users"] / cfg["items"] * k * k + 2.7 * k ** 3
+    cores = os.cpu_count() or 1
+    budget = 3.0e9 * cores * scale  # a few seconds per half at ~1 GFMA/s/core
+    nu = int(min(cfg["users"], max(1000, budget / per_user)))
+    ni = int(min(cfg["items"], max(200, budget / per_item)))
+    return nu, ni
+
+
+def reference_arm(args, cfg, name):
+    """--impl reference: no GPU code on this path. Workload rows from the numpy twin of the
+    device generator (oracle/synth.py)."""
+    from oracle import synth
+    U, I, nnz, k = cfg["users"], cfg["items"], cfg["nnz_per_user"], cfg["k"]
+    nu, ni = sample_sizes(cfg)
+    user_rows = synth.synth_rows(0, nu, I, nnz, seed=SEED, neg_fraction=0.0)
+    Y = synth.unit_rows(I, k, seed=SEED)
+    # Item sample: the first `ni` items. Stratum j of the generator covers items
+    # [j*I/nnz, (j+1)*I/nnz); scan every user's draw in the strata that intersect the sample.
+    item_ptr, item_idx, item_val = synth_item_rows(cfg, ni)
+    # X for the Y-half: timing is data-independent; tile a block of unit rows to full height.
+    blk = synth.unit_rows(min(U, 1_000_000), k, seed=SEED + 1)
+    X = np.tile(blk, ((U + blk.shape[0] - 1) // blk.shape[0], 1))[:U]
+    results = []
+    for step in range(args.warmup + args.steps):
+        r = cpu_baseline_from_sample(cfg, user_rows, (item_ptr, item_idx, item_val), Y, X,
+                                     "per bench step one such sample")
+        if step >= args.warmup:
+            results.append(r)
+    t_iter = float(np.mean([r["seconds_per_iteration_extrapolated"] for r in results]))
+    cb = results[-1]
+    cb["value"] = 1.0 / t_iter
+    line = {
+        "impl": "reference", "metric": "ALS iterations/sec", "value": 1.0 / t_iter,
+        "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_iter * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[name], "users": U, "items": I,
+                   "nnz_per_user": nnz, "features": k, "alpha": 1.0, "lambda": 0.1,
+                   "seed": SEED},
+        "updated_rows_per_s": (U + I) / t_iter,
+        "cpu_baseline": cb,
+        "e2e": {"value": 1.0 / t_iter, "unit": "iterations/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def synth_item_rows(cfg, ni):
+    from oracle import synth
+    U, I, nnz = cfg["users"], cfg["items"], cfg["nnz_per_user"]
+    strata = sorted({min(nnz - 1, (i * nnz) // I) for i in (0, ni - 1)})
+    strata = list(range(strata[0], strata[-1] + 1))
+    rows_l, items_l, vals_l = [], [], []
+    chunk = 2_000_000
+    for j in strata:
+        lo, hi = (j * I) // nnz, ((j + 1) * I) // nnz
+        for u0 in range(0, U, chunk):
+            us = np.arange(u0, min(U, u0 + chunk), dtype=np.uint64)
+            h = synth.synth_hash(SEED, us, np.full(us.size, j, dtype=np.uint64))
+            it = lo + ((h >> np.uint64(32)) % np.uint64(hi - lo)).astype(np.int64)
+            keep = it < ni
+            s = (1 + ((h & np.uint64(0xffff)) % np.uint64(5)).astype(np.int64)).astype(np.float32)
+            rows_l.append(us[keep].astype(np.int32)); items_l.append(it[keep]); vals_l.append(s[keep])
+    rows = np.concatenate(rows_l); items = np.concatenate(items_l); vals = np.concatenate(vals_l)
+    order = np.lexsort((rows, items))
+    ptr = np.zeros(ni + 1, dtype=np.int64)
+    np.cumsum(np.bincount(items, minlength=ni), out=ptr[1:])
+    return ptr, np.ascontiguousarray(rows[order]), np.ascontiguousarray(vals[order])
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    name = args.config
+    cfg = CONFIGS[name]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            reference_arm(args, cfg, name)
+        return 0
+
+    import torch
+    import myrrix_recommender_b200 as M
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device visible (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    U, I, nnz_pu, k = cfg["users"], cfg["items"], cfg["nnz_per_user"], cfg["k"]
+    nnz = U * nnz_pu
+    kernel = {"auto": 0, "simt": 1, "tcgen05": 2}[args.kernel]
+
+    als = M.NativeALS(k, device=local_rank, kernel=kernel)
+    stream = torch.cuda.current_stream()
+    als.set_stream(stream.cuda_stream)
+    if world > 1:
+        import torch.distributed as dist
+        uid = [M.factorizer.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        als.comm_init(rank, world, uid[0])
+    als.synth_interactions(U, I, nnz_pu, seed=SEED, neg_fraction=0.0)
+    als.synth_y0(seed=SEED)
+    h_y0 = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        import ctypes as C
+        h_y0 = torch.empty((I, k), dtype=torch.float32, pin_memory=True)
+        als.check(als.lib.als_get_y(als.h, C.cast(h_y0.data_ptr(), C.POINTER(C.c_float))))
+    info = als.info()
+    kernel_name = {1: "simt", 2: "tcgen05"}[info.kernel]
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: W warm-up + exactly K timed iterations -----------------
+    als.iterate(args.warmup)
+    als.sync()
+    als.profile(True)
+    als.timings(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    als.iterate(args.steps)
+    ev1.record(stream)
+    barrier()
+    als.sync()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    tm = als.timings(reset=True)
+    als.profile(False)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- roofline of the dominant kernel (row update), timed live with CUDA events --------
+    peak, peak_src = measured_peak()
+    x_ms = tm.update_x_ms / max(tm.n_half_x, 1)
+    y_ms = tm.update_y_ms / max(tm.n_half_y, 1)
+    bx = update_launch_bytes(U // world, nnz // world, k)
+    by = update_launch_bytes(I // world, nnz // world, k)
+    dom = "x" if x_ms >= y_ms else "y"
+    dom_ms, dom_b = (x_ms, bx) if dom == "x" else (y_ms, by)
+    achieved = dom_b / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f).get("%s_%s_%s" % (name, kernel_name, dom))
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic,
+        "kernel": "row_update_%s (%s half)" % (kernel_name, "X<-Y" if dom == "x" else "Y<-X"),
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_b,
+        "avg_launch_ms": dom_ms,
+        "other_half": {"avg_launch_ms": y_ms if dom == "x" else x_ms,
+                       "algorithmic_bytes_per_launch": by if dom == "x" else bx},
+        "gramian_ms_per_iteration": tm.gramian_ms / args.steps,
+        "exchange_ms_per_iteration": tm.exchange_ms / args.steps,
+        "iteration_frac_of_hbm_roof": algorithmic_bytes(U, I, nnz, k) / world /
+                                      (ms_per_step * 1e-3) / 1e9 / peak,
+    }
+    gpu_launches = int(tm.launches)
+
+    # ---- e2e through the C ABI with HOST buffers ------------------------------------------
+    e2e = None
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        # untimed: bring the device-generated workload to pinned host memory
+        h_ptr = torch.empty(U + 1, dtype=torch.int64, pin_memory=True)
+        h_idx = torch.empty(nnz, dtype=torch.int32, pin_memory=True)
+        h_val = torch.empty(nnz, dtype=torch.float32, pin_memory=True)
+        h_x = torch.empty((U, k), dtype=torch.float32, pin_memory=True)
+        h_y = torch.empty((I, k), dtype=torch.float32, pin_memory=True)
+        import ctypes as C
+        lib = als.lib
+        als.check(lib.als_get_interactions(als.h, C.cast(h_ptr.data_ptr(), C.POINTER(C.c_int64)),
+                                           C.cast(h_idx.data_ptr(), C.POINTER(C.c_int32)),
+                                           C.cast(h_val.data_ptr(), C.POINTER(C.c_float))))
+        als.close()
+
+        def one_call():
+            a = M.NativeALS(k, device=local_rank, kernel=kernel)
+            a.set_stream(stream.cuda_stream)
+            a.check(lib.als_set_interactions(a.h, U, I, C.cast(h_ptr.data_ptr(), C.POINTER(C.c_int64)),
+                                             C.cast(h_idx.data_ptr(), C.POINTER(C.c_int32)),
+                                             C.cast(h_val.data_ptr(), C.POINTER(C.c_float))))
+            a.n_users, a.n_items = U, I
+            a.check(lib.als_set_y(a.h, C.cast(h_y0.data_ptr(), C.POINTER(C.c_float))))
+            a.iterate(args.steps)
+            a.check(lib.als_get_x(a.h, C.cast(h_x.data_ptr(), C.POINTER(C.c_float))))
+            a.check(lib.als_get_y(a.h, C.cast(h_y.data_ptr(), C.POINTER(C.c_float))))
+            a.close()
+
+        one_call()  # warm-up (allocator, first-touch)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        one_call()
+        torch.cuda.synchronize()
+        t_call = time.perf_counter() - t0
+        h2d = (U + 1) * 8 + nnz * 8 + I * k * 4
+        d2h = (U + I) * k * 4
+        e2e = {"value": args.steps / t_call, "unit": "iterations/s",
+               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+               "call": "one factorizer call: upload CSR + Y0 from pinned host memory, build the "
+                       "by-item orientation on the device, %d iterations, read X and Y back"
+                       % args.steps,
+               "seconds_per_call": t_call, "finite": bool(torch.isfinite(h_x[:1000]).all())}
+        if not args.no_cpu_baseline:
+            nu, ni = sample_sizes(cfg, scale=3.0)  # ~15-25 s of CPU work in total
+            ptr_np = h_ptr.numpy()
+            e1 = int(ptr_np[nu])
+            user_rows = (ptr_np[:nu + 1].copy(), h_idx.numpy()[:e1].copy(), h_val.numpy()[:e1].copy())
+            item_rows = synth_item_rows(cfg, ni)
+            cpu_baseline = cpu_baseline_from_sample(cfg, user_rows, item_rows, h_y0.numpy(),
+                                                    h_x.numpy(), "timed once on rank 0")
+    elif rank == 0:
+        als.close()
+
+    if rank == 0:
+        line = {
+            "metric": "ALS iterations/sec", "value": value, "unit": "iterations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[name], "users": U, "items": I,
+                       "nnz_per_user": nnz_pu, "features": k, "alpha": 1.0, "lambda": 0.1,
+                       "seed": SEED, "kernel": kernel_name,
+                       "l2": "inputs (>= %.1f GB per half) exceed the 126 MB L2; no flush needed"
+                             % (nnz * 8 / 1e9),
+                       "parallelism": "1 GPU" if world == 1 else
+                                      "users/items range-sharded over %d GPUs, factor all-gather" % world},
+            "updated_rows_per_s": (U + I) * value,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": gpu_launches, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,870 @@
+// als_abi.cu -- the C ABI (include/myrrix_als.h) over the sm_100a kernels.
+//
+// Plain CUDA runtime: no torch types anywhere in this library.  One handle owns
+// all HBM: both orientations of R (CSR by user, CSR by item), the two factor
+// matrices with a padded row stride, the fp64 Gramian and its partials.
+#include <cub/device/device_radix_sort.cuh>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "aux_kernels.cuh"
+#include "common.cuh"
+#include "gramian.cuh"
+#include "row_update_simt.cuh"
+#include "row_update_umma.cuh"
+
+using namespace als;
+
+// ---------------------------------------------------------------------------
+// NCCL is resolved at run time (dlopen) so the library loads on a box without it
+// and a single-GPU caller never pays for it.
+#include <nccl.h>
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+bool load_nccl() {
+  if (g_nccl.ok) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return false;
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(g_nccl.lib, "ncclAllGather");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllGather &&
+              g_nccl.GetErrorString;
+  return g_nccl.ok;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------
+struct Csr {
+  long long* ptr = nullptr;  // [rows+1]
+  int* idx = nullptr;        // [nnz]
+  float* val = nullptr;      // [nnz]
+  long long rows = 0;        // local rows
+  long long nnz = 0;
+  long long row_begin = 0;   // global index of local row 0
+};
+
+struct als_handle {
+  als_config cfg;
+  int k = 0, ks = 0;
+  int kernel = ALS_KERNEL_SIMT;
+  int device = 0;
+  int sm_count = 0;
+  long long n_users = 0, n_items = 0;      // global
+  long long users_alloc = 0, items_alloc = 0;  // rows allocated (padded to world blocks)
+  Csr by_user, by_item;
+  bool have_by_item = false;
+  float* X = nullptr;
+  float* Y = nullptr;
+  double* G = nullptr;
+  double* G_partial = nullptr;
+  int g_partials = 0;
+  DeviceStatus* d_status = nullptr;
+  unsigned long long* d_ticket = nullptr;
+  double* d_scratch = nullptr;  // rank kernel scratch + probe output
+  int* d_rank = nullptr;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  long long device_bytes = 0;
+  // multi-GPU
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  // profiling
+  bool profile = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  als_timings tm;
+  struct PendingEv { cudaEvent_t a, b; int kind; };
+  PendingEv* pending = nullptr;
+  int n_pending = 0, cap_pending = 0;
+  int launches = 0;
+  // errors
+  char err[512];
+  int singular_rank = 0;
+  int sticky = ALS_OK;
+};
+
+namespace {
+
+int fail(als_handle* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CU(h, expr)                                                                       \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      const int _c = (_e == cudaErrorMemoryAllocation) ? ALS_E_OOM : ALS_E_CUDA;          \
+      return fail((h), _c, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                  __FILE__, __LINE__);                                                    \
+    }                                                                                     \
+  } while (0)
+
+template <typename T>
+int dev_alloc(als_handle* h, T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, ALS_E_OOM, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T),
+                cudaGetErrorString(e));
+  }
+  h->device_bytes += (long long)(count * sizeof(T));
+  return ALS_OK;
+}
+template <typename T>
+void dev_free(als_handle* h, T** p, size_t count) {
+  if (*p) {
+    cudaFree(*p);
+    h->device_bytes -= (long long)((count ? count : 1) * sizeof(T));
+    *p = nullptr;
+  }
+}
+
+void free_csr(als_handle* h, Csr* c) {
+  dev_free(h, &c->ptr, (size_t)c->rows + 1);
+  dev_free(h, &c->idx, (size_t)c->nnz);
+  dev_free(h, &c->val, (size_t)c->nnz);
+  c->rows = c->nnz = 0;
+}
+
+long long block_rows(long long n, int world) { return (n + world - 1) / world; }
+
+int alloc_factors(als_handle* h) {
+  // Factor replicas are padded to world * block rows so the per-half all-gather is a
+  // plain in-place ncclAllGather of equal blocks.
+  const long long ua = block_rows(h->n_users, h->world) * h->world;
+  const long long ia = block_rows(h->n_items, h->world) * h->world;
+  if (h->X && ua == h->users_alloc && h->Y && ia == h->items_alloc) return ALS_OK;
+  dev_free(h, &h->X, (size_t)h->users_alloc * h->ks);
+  dev_free(h, &h->Y, (size_t)h->items_alloc * h->ks);
+  h->users_alloc = ua;
+  h->items_alloc = ia;
+  int rc;
+  if ((rc = dev_alloc(h, &h->X, (size_t)ua * h->ks)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &h->Y, (size_t)ia * h->ks)) != ALS_OK) return rc;
+  CU(h, cudaMemsetAsync(h->X, 0, sizeof(float) * (size_t)ua * h->ks, h->stream));
+  CU(h, cudaMemsetAsync(h->Y, 0, sizeof(float) * (size_t)ia * h->ks, h->stream));
+  return ALS_OK;
+}
+
+// local block of `n` rows owned by this rank
+void local_block(const als_handle* h, long long n, long long* begin, long long* end) {
+  const long long b = block_rows(n, h->world);
+  *begin = (long long)h->rank * b;
+  if (*begin > n) *begin = n;
+  *end = *begin + b;
+  if (*end > n) *end = n;
+}
+
+// ---- profiling helpers -----------------------------------------------------
+void prof_begin(als_handle* h, cudaEvent_t* a) {
+  *a = nullptr;
+  if (!h->profile) return;
+  cudaEventCreate(a);
+  cudaEventRecord(*a, h->stream);
+}
+void prof_end(als_handle* h, cudaEvent_t a, int kind) {
+  if (!h->profile || !a) return;
+  cudaEvent_t b;
+  cudaEventCreate(&b);
+  cudaEventRecord(b, h->stream);
+  if (h->n_pending == h->cap_pending) {
+    h->cap_pending = h->cap_pending ? 2 * h->cap_pending : 64;
+    h->pending = (als_handle::PendingEv*)realloc(h->pending,
+                                                 sizeof(als_handle::PendingEv) * h->cap_pending);
+  }
+  h->pending[h->n_pending++] = {a, b, kind};
+}
+void prof_drain(als_handle* h) {
+  for (int i = 0; i < h->n_pending; i++) {
+    float ms = 0.f;
+    cudaEventSynchronize(h->pending[i].b);
+    cudaEventElapsedTime(&ms, h->pending[i].a, h->pending[i].b);
+    switch (h->pending[i].kind) {
+      case 0: h->tm.gramian_ms += ms; break;
+      case 1: h->tm.update_x_ms += ms; break;
+      case 2: h->tm.update_y_ms += ms; break;
+      default: h->tm.exchange_ms += ms; break;
+    }
+    cudaEventDestroy(h->pending[i].a);
+    cudaEventDestroy(h->pending[i].b);
+  }
+  h->n_pending = 0;
+}
+
+// ---- kernels launch --------------------------------------------------------
+template <int KS>
+int launch_gramian_t(als_handle* h, const float* M, long long n_rows) {
+  using S = GramShape<KS>;
+  int grid = h->sm_count * 2;
+  const long long chunks = (n_rows + kGramChunk - 1) / kGramChunk;
+  if (chunks < grid) grid = (int)(chunks > 0 ? chunks : 1);
+  const int n_partials = grid * S::GROUPS;
+  if (n_partials > h->g_partials) {
+    dev_free(h, &h->G_partial, (size_t)h->g_partials * h->ks * h->ks);
+    h->g_partials = h->sm_count * 2 * S::GROUPS;
+    int rc = dev_alloc(h, &h->G_partial, (size_t)h->g_partials * h->ks * h->ks);
+    if (rc != ALS_OK) return rc;
+  }
+  gramian_partial_kernel<KS><<<grid, kGramThreads, 0, h->stream>>>(M, n_rows, h->G_partial);
+  const int kk = KS * KS;
+  gramian_reduce_kernel<<<(kk + 255) / 256, 256, 0, h->stream>>>(h->G_partial, n_partials, kk, h->G);
+  h->launches += 2;
+  CU(h, cudaGetLastError());
+  return ALS_OK;
+}
+
+int launch_gramian(als_handle* h, const float* M, long long n_rows) {
+  cudaEvent_t a;
+  prof_begin(h, &a);
+  int rc;
+  switch (h->ks) {
+    case 4: rc = launch_gramian_t<4>(h, M, n_rows); break;
+    case 8: rc = launch_gramian_t<8>(h, M, n_rows); break;
+    case 16: rc = launch_gramian_t<16>(h, M, n_rows); break;
+    case 32: rc = launch_gramian_t<32>(h, M, n_rows); break;
+    case 64: rc = launch_gramian_t<64>(h, M, n_rows); break;
+    case 128: rc = launch_gramian_t<128>(h, M, n_rows); break;
+    default: return fail(h, ALS_E_UNSUPPORTED, "padded feature count %d unsupported", h->ks);
+  }
+  prof_end(h, a, 0);
+  return rc;
+}
+
+template <int KS>
+int launch_simt_t(als_handle* h, const RowUpdateParams& p) {
+  using S = SimtShape<KS>;
+  const size_t smem = S::smem_bytes();
+  static bool configured = false;
+  static int blocks_per_sm = 1;
+  if (!configured) {
+    CU(h, cudaFuncSetAttribute(row_update_simt_kernel<KS>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, row_update_simt_kernel<KS>,
+                                                        kSimtThreads, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    configured = true;
+  }
+  long long grid = (long long)h->sm_count * blocks_per_sm;
+  if (grid > p.n_rows) grid = p.n_rows > 0 ? p.n_rows : 1;
+  row_update_simt_kernel<KS><<<(int)grid, kSimtThreads, smem, h->stream>>>(p);
+  h->launches += 1;
+  CU(h, cudaGetLastError());
+  return ALS_OK;
+}
+
+int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, int which) {
+  RowUpdateParams p;
+  p.row_ptr = R.ptr;
+  p.col_idx = R.idx;
+  p.val = R.val;
+  p.n_rows = R.rows;
+  p.row_offset = R.row_begin;
+  p.M = M;
+  p.G = h->G;
+  p.out = out;
+  p.k = h->k;
+  p.alpha = (float)h->cfg.alpha;
+  p.lambda_alpha = h->cfg.lambda * h->cfg.alpha;
+  p.reconstruct_r = h->cfg.reconstruct_r;
+  p.loss_ignores_unspecified = h->cfg.loss_ignores_unspecified;
+  p.threshold = (float)h->cfg.singularity_threshold;
+  p.which = which;
+  p.status = h->d_status;
+  p.ticket = h->d_ticket;
+  CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned long long), h->stream));
+  cudaEvent_t a;
+  prof_begin(h, &a);
+  int rc = ALS_OK;
+  if (h->kernel == ALS_KERNEL_TCGEN05) {
+    rc = launch_row_update_umma(h->ks, p, h->sm_count, h->stream, h->err, sizeof(h->err));
+    if (rc == ALS_OK) h->launches += 1;
+  } else {
+    switch (h->ks) {
+      case 4: rc = launch_simt_t<4>(h, p); break;
+      case 8: rc = launch_simt_t<8>(h, p); break;
+      case 16: rc = launch_simt_t<16>(h, p); break;
+      case 32: rc = launch_simt_t<32>(h, p); break;
+      case 64: rc = launch_simt_t<64>(h, p); break;
+      case 128: rc = launch_simt_t<128>(h, p); break;
+      default: rc = fail(h, ALS_E_UNSUPPORTED, "padded feature count %d unsupported", h->ks);
+    }
+  }
+  prof_end(h, a, which == 0 ? 1 : 2);
+  return rc;
+}
+
+int exchange(als_handle* h, float* F, long long n_global) {
+  if (h->world == 1) return ALS_OK;
+  cudaEvent_t a;
+  prof_begin(h, &a);
+  const long long b = block_rows(n_global, h->world);
+  const size_t count = (size_t)b * h->ks;
+  ncclResult_t r = g_nccl.AllGather(F + (size_t)h->rank * count, F, count, ncclFloat, h->comm,
+                                    h->stream);
+  if (r != ncclSuccess) return fail(h, ALS_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(r));
+  h->launches += 1;
+  prof_end(h, a, 3);
+  return ALS_OK;
+}
+
+// Build the by-item orientation on the device: stable LSD radix sort of
+// (column key, row<<32|value) so each column keeps ascending row order.
+int build_transpose(als_handle* h) {
+  Csr& A = h->by_user;
+  Csr& T = h->by_item;
+  free_csr(h, &T);
+  T.rows = h->n_items;
+  T.nnz = A.nnz;
+  T.row_begin = 0;
+  int rc;
+  if ((rc = dev_alloc(h, &T.ptr, (size_t)T.rows + 1)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &T.idx, (size_t)T.nnz)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &T.val, (size_t)T.nnz)) != ALS_OK) return rc;
+  if (A.nnz == 0) {
+    CU(h, cudaMemsetAsync(T.ptr, 0, sizeof(long long) * ((size_t)T.rows + 1), h->stream));
+    h->have_by_item = true;
+    return ALS_OK;
+  }
+  if (A.nnz >= (1LL << 31)) return fail(h, ALS_E_UNSUPPORTED, "nnz >= 2^31 per device");
+  int *keys_in = nullptr, *keys_out = nullptr;
+  unsigned long long *pk_in = nullptr, *pk_out = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  const size_t n = (size_t)A.nnz;
+  auto cleanup = [&]() {
+    dev_free(h, &keys_in, n); dev_free(h, &keys_out, n);
+    dev_free(h, &pk_in, n); dev_free(h, &pk_out, n);
+    if (tmp) { cudaFree(tmp); h->device_bytes -= (long long)tmp_bytes; }
+  };
+  if ((rc = dev_alloc(h, &keys_in, n)) != ALS_OK || (rc = dev_alloc(h, &keys_out, n)) != ALS_OK ||
+      (rc = dev_alloc(h, &pk_in, n)) != ALS_OK || (rc = dev_alloc(h, &pk_out, n)) != ALS_OK) {
+    cleanup();
+    return rc;
+  }
+  expand_rows_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(A.ptr, A.rows, A.idx, A.val, keys_in,
+                                                            pk_in);
+  int end_bit = 1;
+  while ((1LL << end_bit) < h->n_items && end_bit < 31) end_bit++;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, pk_in,
+                                                  pk_out, (int)n, 0, end_bit, h->stream);
+  if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+  if (e == cudaSuccess) {
+    h->device_bytes += (long long)tmp_bytes;
+    e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, pk_in, pk_out, (int)n, 0,
+                                        end_bit, h->stream);
+  }
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(h, e == cudaErrorMemoryAllocation ? ALS_E_OOM : ALS_E_CUDA, "transpose sort: %s",
+                cudaGetErrorString(e));
+  }
+  build_ptr_unpack_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(keys_out, pk_out, A.nnz, T.rows,
+                                                                 T.ptr, T.idx, T.val);
+  h->launches += 3;
+  e = cudaStreamSynchronize(h->stream);
+  cleanup();
+  if (e != cudaSuccess) return fail(h, ALS_E_CUDA, "transpose: %s", cudaGetErrorString(e));
+  h->have_by_item = true;
+  return ALS_OK;
+}
+
+int upload_csr(als_handle* h, Csr* c, long long rows, long long row_begin, const long long* ptr,
+               const int* idx, const float* val, cudaMemcpyKind kind) {
+  free_csr(h, c);
+  long long first = 0, last = 0;
+  if (kind == cudaMemcpyHostToDevice) {
+    first = ptr[0];
+    last = ptr[rows];
+  } else {
+    CU(h, cudaMemcpy(&first, ptr, sizeof(long long), cudaMemcpyDeviceToHost));
+    CU(h, cudaMemcpy(&last, ptr + rows, sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  if (first != 0 || last < 0) return fail(h, ALS_E_ARG, "row_ptr must start at 0 and be non-negative");
+  if (last > 0 && (!idx || !val)) return fail(h, ALS_E_ARG, "null col_idx/val with nnz > 0");
+  c->rows = rows;
+  c->nnz = last;
+  c->row_begin = row_begin;
+  int rc;
+  if ((rc = dev_alloc(h, &c->ptr, (size_t)rows + 1)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &c->idx, (size_t)c->nnz)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &c->val, (size_t)c->nnz)) != ALS_OK) return rc;
+  CU(h, cudaMemcpyAsync(c->ptr, ptr, sizeof(long long) * ((size_t)rows + 1), kind, h->stream));
+  CU(h, cudaMemcpyAsync(c->idx, idx, sizeof(int) * (size_t)c->nnz, kind, h->stream));
+  CU(h, cudaMemcpyAsync(c->val, val, sizeof(float) * (size_t)c->nnz, kind, h->stream));
+  return ALS_OK;
+}
+
+int check_ready(als_handle* h) {
+  if (!h) return ALS_E_ARG;
+  if (!h->by_user.ptr || !h->have_by_item || !h->X || !h->Y)
+    return fail(h, ALS_E_STATE, "interactions not set");
+  return ALS_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int als_abi_version(void) { return MYRRIX_ALS_ABI_VERSION; }
+
+int als_config_default(als_config* cfg) {
+  if (!cfg) return ALS_E_ARG;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->struct_size = (int32_t)sizeof(als_config);
+  cfg->features = 30;       // MatrixFactorizer.DEFAULT_FEATURES (MatrixFactorizer.java:34)
+  cfg->alpha = 1.0;         // AlternatingLeastSquares.DEFAULT_ALPHA (:71)
+  cfg->lambda = 0.1;        // DEFAULT_LAMBDA (:73)
+  cfg->singularity_threshold = 1.0e-5;  // LinearSystemSolver.java:33-34
+  cfg->device = 0;
+  cfg->kernel = ALS_KERNEL_AUTO;
+  return ALS_OK;
+}
+
+int als_create(const als_config* cfg, als_handle** out) {
+  if (!cfg || !out) return ALS_E_ARG;
+  *out = nullptr;
+  if (cfg->struct_size != (int32_t)sizeof(als_config)) return ALS_E_ARG;
+  // Preconditions of the reference constructor (AlternatingLeastSquares.java:137-141).
+  if (cfg->features <= 0 || cfg->features > kMaxFeatures) return ALS_E_ARG;
+  if (!(cfg->alpha == cfg->alpha) || !(cfg->lambda == cfg->lambda)) return ALS_E_ARG;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return ALS_E_CUDA;  // no CPU fallback: without a GPU this library does not run
+  }
+  if (cfg->device < 0 || cfg->device >= n_dev) return ALS_E_ARG;
+  als_handle* h = new (std::nothrow) als_handle();
+  if (!h) return ALS_E_OOM;
+  h->cfg = *cfg;
+  h->err[0] = 0;
+  memset(&h->tm, 0, sizeof(h->tm));
+  h->tm.struct_size = (int32_t)sizeof(als_timings);
+  h->k = cfg->features;
+  h->ks = padded_features(cfg->features);
+  h->device = cfg->device;
+  *out = h;
+  CU(h, cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CU(h, cudaGetDeviceProperties(&prop, h->device));
+  h->sm_count = prop.multiProcessorCount;
+  if (prop.major != 10) {
+    return fail(h, ALS_E_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only",
+                prop.major, prop.minor);
+  }
+  // kernel selection
+  const bool umma_ok = umma_supported(h->ks) && !cfg->loss_ignores_unspecified;
+  if (cfg->kernel == ALS_KERNEL_TCGEN05 && !umma_ok)
+    return fail(h, ALS_E_UNSUPPORTED, "tcgen05 kernel not available for features=%d", cfg->features);
+  h->kernel = (cfg->kernel == ALS_KERNEL_SIMT) ? ALS_KERNEL_SIMT
+              : (umma_ok ? ALS_KERNEL_TCGEN05 : ALS_KERNEL_SIMT);
+  CU(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  int rc;
+  if ((rc = dev_alloc(h, &h->G, (size_t)h->ks * h->ks)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &h->d_status, 1)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &h->d_ticket, 1)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &h->d_rank, 1)) != ALS_OK) return rc;
+  const size_t scratch = (size_t)2 * h->k * h->k + 2 * h->k + 1;
+  if ((rc = dev_alloc(h, &h->d_scratch, scratch > 10000 ? scratch : 10000)) != ALS_OK) return rc;
+  CU(h, cudaMemsetAsync(h->d_status, 0, sizeof(DeviceStatus), h->stream));
+  CU(h, cudaMemsetAsync(h->G, 0, sizeof(double) * h->ks * h->ks, h->stream));
+  return ALS_OK;
+}
+
+int als_destroy(als_handle* h) {
+  if (!h) return ALS_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  prof_drain(h);
+  free(h->pending);
+  if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+  free_csr(h, &h->by_user);
+  free_csr(h, &h->by_item);
+  cudaFree(h->X); cudaFree(h->Y); cudaFree(h->G); cudaFree(h->G_partial);
+  cudaFree(h->d_status); cudaFree(h->d_ticket); cudaFree(h->d_rank); cudaFree(h->d_scratch);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return ALS_OK;
+}
+
+int als_set_stream(als_handle* h, void* cuda_stream) {
+  if (!h) return ALS_E_ARG;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return ALS_OK;
+}
+
+static int set_dims(als_handle* h, int64_t n_users, int64_t n_items) {
+  if (n_users <= 0 || n_items <= 0 || n_users >= (1LL << 31) || n_items >= (1LL << 31))
+    return fail(h, ALS_E_ARG, "n_users/n_items must be in [1, 2^31)");
+  h->n_users = n_users;
+  h->n_items = n_items;
+  return alloc_factors(h);
+}
+
+int als_set_interactions(als_handle* h, int64_t n_users, int64_t n_items, const int64_t* row_ptr,
+                         const int32_t* col_idx, const float* val) {
+  if (!h || !row_ptr) return ALS_E_ARG;
+  CU(h, cudaSetDevice(h->device));
+  int rc = set_dims(h, n_users, n_items);
+  if (rc != ALS_OK) return rc;
+  long long ub, ue;
+  local_block(h, h->n_users, &ub, &ue);
+  h->have_by_item = false;
+  rc = upload_csr(h, &h->by_user, ue - ub, ub, (const long long*)row_ptr, col_idx, val,
+                  cudaMemcpyHostToDevice);
+  if (rc != ALS_OK) return rc;
+  if (h->world == 1) return build_transpose(h);
+  CU(h, cudaStreamSynchronize(h->stream));
+  return ALS_OK;  // sharded: caller must follow with als_set_interactions_by_column
+}
+
+int als_set_interactions_by_column(als_handle* h, const int64_t* col_ptr, const int32_t* row_idx,
+                                   const float* val) {
+  if (!h || !col_ptr) return ALS_E_ARG;
+  if (!h->by_user.ptr) return fail(h, ALS_E_STATE, "call als_set_interactions first");
+  CU(h, cudaSetDevice(h->device));
+  long long ib, ie;
+  local_block(h, h->n_items, &ib, &ie);
+  int rc = upload_csr(h, &h->by_item, ie - ib, ib, (const long long*)col_ptr, row_idx, val,
+                      cudaMemcpyHostToDevice);
+  if (rc != ALS_OK) return rc;
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->have_by_item = true;
+  return ALS_OK;
+}
+
+int als_set_interactions_device(als_handle* h, int64_t n_users, int64_t n_items,
+                                const int64_t* d_row_ptr, const int32_t* d_col_idx,
+                                const float* d_val) {
+  if (!h || !d_row_ptr) return ALS_E_ARG;
+  if (h->world != 1) return fail(h, ALS_E_UNSUPPORTED, "device upload is single-GPU only");
+  CU(h, cudaSetDevice(h->device));
+  int rc = set_dims(h, n_users, n_items);
+  if (rc != ALS_OK) return rc;
+  h->have_by_item = false;
+  rc = upload_csr(h, &h->by_user, n_users, 0, (const long long*)d_row_ptr, d_col_idx, d_val,
+                  cudaMemcpyDeviceToDevice);
+  if (rc != ALS_OK) return rc;
+  return build_transpose(h);
+}
+
+static int set_factor(als_handle* h, float* dst, long long rows, const float* src) {
+  if (!h || !src) return ALS_E_ARG;
+  if (!dst) return fail(h, ALS_E_STATE, "interactions not set");
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaMemcpy2DAsync(dst, sizeof(float) * h->ks, src, sizeof(float) * h->k,
+                          sizeof(float) * h->k, (size_t)rows, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return ALS_OK;
+}
+int als_set_y(als_handle* h, const float* y) { return set_factor(h, h ? h->Y : nullptr, h ? h->n_items : 0, y); }
+int als_set_x(als_handle* h, const float* x) { return set_factor(h, h ? h->X : nullptr, h ? h->n_users : 0, x); }
+
+static int get_factor(als_handle* h, const float* src, long long rows, float* out) {
+  if (!h || !out) return ALS_E_ARG;
+  if (!src) return fail(h, ALS_E_STATE, "interactions not set");
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaMemcpy2DAsync(out, sizeof(float) * h->k, src, sizeof(float) * h->ks,
+                          sizeof(float) * h->k, (size_t)rows, cudaMemcpyDeviceToHost, h->stream));
+  return als_sync(h);
+}
+int als_get_x(als_handle* h, float* out) { return get_factor(h, h ? h->X : nullptr, h ? h->n_users : 0, out); }
+int als_get_y(als_handle* h, float* out) { return get_factor(h, h ? h->Y : nullptr, h ? h->n_items : 0, out); }
+
+int als_half_x(als_handle* h) {
+  int rc = check_ready(h);
+  if (rc != ALS_OK) return rc;
+  CU(h, cudaSetDevice(h->device));
+  // RealMatrix YTY = MatrixUtils.transposeTimesSelf(Y)  (ALS.java:342)
+  if ((rc = launch_gramian(h, h->Y, h->n_items)) != ALS_OK) return rc;
+  // addWorkers(RbyRow, Y, YTY, X, ...)  (ALS.java:344)
+  if ((rc = launch_row_update(h, h->by_user, h->Y, h->X, 0)) != ALS_OK) return rc;
+  h->tm.n_half_x++;
+  return exchange(h, h->X, h->n_users);
+}
+
+int als_half_y(als_handle* h) {
+  int rc = check_ready(h);
+  if (rc != ALS_OK) return rc;
+  CU(h, cudaSetDevice(h->device));
+  if ((rc = launch_gramian(h, h->X, h->n_users)) != ALS_OK) return rc;   // ALS.java:369
+  if ((rc = launch_row_update(h, h->by_item, h->X, h->Y, 1)) != ALS_OK) return rc;  // :371
+  h->tm.n_half_y++;
+  return exchange(h, h->Y, h->n_items);
+}
+
+int als_iterate(als_handle* h, int32_t n_iterations) {
+  if (!h || n_iterations < 0) return ALS_E_ARG;
+  for (int it = 0; it < n_iterations; it++) {
+    int rc = als_half_x(h);
+    if (rc != ALS_OK) return rc;
+    rc = als_half_y(h);
+    if (rc != ALS_OK) return rc;
+  }
+  return ALS_OK;
+}
+
+int als_probe(als_handle* h, const int32_t* users, int32_t n_users, const int32_t* items,
+              int32_t n_items, double* out) {
+  int rc = check_ready(h);
+  if (rc != ALS_OK) return rc;
+  if (!users || !items || !out || n_users < 0 || n_items < 0) return ALS_E_ARG;
+  const long long n = (long long)n_users * n_items;
+  if (n == 0) return ALS_OK;
+  if (n > 1000000) return fail(h, ALS_E_ARG, "probe too large");
+  for (int i = 0; i < n_users; i++)
+    if (users[i] < 0 || users[i] >= h->n_users) return fail(h, ALS_E_ARG, "probe user out of range");
+  for (int j = 0; j < n_items; j++)
+    if (items[j] < 0 || items[j] >= h->n_items) return fail(h, ALS_E_ARG, "probe item out of range");
+  CU(h, cudaSetDevice(h->device));
+  int *d_u = nullptr, *d_i = nullptr;
+  double* d_out = nullptr;
+  CU(h, cudaMalloc(&d_u, sizeof(int) * n_users));
+  CU(h, cudaMalloc(&d_i, sizeof(int) * n_items));
+  CU(h, cudaMalloc(&d_out, sizeof(double) * n));
+  cudaMemcpyAsync(d_u, users, sizeof(int) * n_users, cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(d_i, items, sizeof(int) * n_items, cudaMemcpyHostToDevice, h->stream);
+  probe_kernel<<<(int)((n + 127) / 128), 128, 0, h->stream>>>(h->X, h->Y, h->ks, h->k, d_u, n_users,
+                                                             d_i, n_items, d_out);
+  h->launches += 1;
+  cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_u); cudaFree(d_i); cudaFree(d_out);
+  if (e != cudaSuccess) return fail(h, ALS_E_CUDA, "probe: %s", cudaGetErrorString(e));
+  return ALS_OK;
+}
+
+int als_gramian(als_handle* h, int32_t which, double* out) {
+  int rc = check_ready(h);
+  if (rc != ALS_OK) return rc;
+  if (!out || (which != 0 && which != 1)) return ALS_E_ARG;
+  CU(h, cudaSetDevice(h->device));
+  rc = which == 0 ? launch_gramian(h, h->X, h->n_users) : launch_gramian(h, h->Y, h->n_items);
+  if (rc != ALS_OK) return rc;
+  CU(h, cudaMemcpy2DAsync(out, sizeof(double) * h->k, h->G, sizeof(double) * h->ks,
+                          sizeof(double) * h->k, (size_t)h->k, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return ALS_OK;
+}
+
+int als_sync(als_handle* h) {
+  if (!h) return ALS_E_ARG;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  prof_drain(h);
+  if (h->sticky != ALS_OK) return h->sticky;
+  DeviceStatus st;
+  CU(h, cudaMemcpy(&st, h->d_status, sizeof(st), cudaMemcpyDeviceToHost));
+  if (st.code == ALS_OK) return ALS_OK;
+  h->sticky = st.code;
+  const char* half = st.which == 0 ? "X" : "Y";
+  if (st.code == ALS_E_SINGULAR) {
+    // apparent rank of the offending W_u (rare path)
+    const Csr& R = st.which == 0 ? h->by_user : h->by_item;
+    const float* M = st.which == 0 ? h->Y : h->X;
+    singular_rank_kernel<<<1, 1, 0, h->stream>>>(R.ptr, R.idx, R.val, st.row - R.row_begin, M, h->G,
+                                                 h->ks, h->k, h->cfg.alpha,
+                                                 h->cfg.lambda * h->cfg.alpha, h->cfg.reconstruct_r,
+                                                 h->cfg.loss_ignores_unspecified, h->d_scratch,
+                                                 h->d_rank);
+    int rank = 0;
+    cudaMemcpyAsync(&rank, h->d_rank, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    h->singular_rank = rank;
+    return fail(h, ALS_E_SINGULAR,
+                "%s-half row %lld: %d x %d matrix is near-singular (pivot %g <= threshold %g). "
+                "Apparent rank: %d",
+                half, st.row, h->k, h->k, (double)st.pivot, h->cfg.singularity_threshold, rank);
+  }
+  return fail(h, st.code, "%s-half row %lld produced a non-finite factor value", half, st.row);
+}
+
+const char* als_last_error(const als_handle* h) { return h ? h->err : "null handle"; }
+int als_singular_rank(const als_handle* h) { return h ? h->singular_rank : 0; }
+
+int als_get_info(const als_handle* h, als_info* out) {
+  if (!h || !out) return ALS_E_ARG;
+  memset(out, 0, sizeof(*out));
+  out->struct_size = (int32_t)sizeof(als_info);
+  out->features = h->k;
+  out->padded_features = h->ks;
+  out->kernel = h->kernel;
+  out->n_users = h->n_users;
+  out->n_items = h->n_items;
+  out->nnz = h->by_user.nnz;
+  out->device_bytes = h->device_bytes;
+  out->sm_count = h->sm_count;
+  out->world_size = h->world;
+  out->rank = h->rank;
+  return ALS_OK;
+}
+
+int als_profile_enable(als_handle* h, int32_t on) {
+  if (!h) return ALS_E_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  prof_drain(h);
+  h->profile = on != 0;
+  return ALS_OK;
+}
+
+int als_get_timings(als_handle* h, als_timings* out, int32_t reset) {
+  if (!h || !out) return ALS_E_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  prof_drain(h);
+  h->tm.launches = h->launches;
+  *out = h->tm;
+  if (reset) {
+    memset(&h->tm, 0, sizeof(h->tm));
+    h->tm.struct_size = (int32_t)sizeof(als_timings);
+    h->launches = 0;
+  }
+  return ALS_OK;
+}
+
+// ---- synthetic workload -----------------------------------------------------
+int als_synth_interactions(als_handle* h, int64_t n_users, int64_t n_items, int32_t nnz_per_user,
+                           uint64_t seed, double neg_fraction) {
+  if (!h) return ALS_E_ARG;
+  if (nnz_per_user <= 0 || nnz_per_user > n_items) return fail(h, ALS_E_ARG, "bad nnz_per_user");
+  if (neg_fraction < 0.0 || neg_fraction > 1.0) return fail(h, ALS_E_ARG, "bad neg_fraction");
+  if (h->world != 1) return fail(h, ALS_E_UNSUPPORTED, "sharded synthesis not implemented yet");
+  CU(h, cudaSetDevice(h->device));
+  int rc = set_dims(h, n_users, n_items);
+  if (rc != ALS_OK) return rc;
+  Csr& A = h->by_user;
+  free_csr(h, &A);
+  h->have_by_item = false;
+  A.rows = n_users;
+  A.nnz = (long long)n_users * nnz_per_user;
+  A.row_begin = 0;
+  if ((rc = dev_alloc(h, &A.ptr, (size_t)A.rows + 1)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &A.idx, (size_t)A.nnz)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &A.val, (size_t)A.nnz)) != ALS_OK) return rc;
+  const unsigned int thr = (unsigned int)(neg_fraction * 16777216.0);
+  synth_rows_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(0, A.rows, n_items, nnz_per_user, seed,
+                                                           thr, A.ptr, A.idx, A.val);
+  h->launches += 1;
+  CU(h, cudaGetLastError());
+  return build_transpose(h);
+}
+
+int als_synth_y0(als_handle* h, uint64_t seed) {
+  int rc = check_ready(h);
+  if (rc != ALS_OK) return rc;
+  CU(h, cudaSetDevice(h->device));
+  synth_y0_kernel<<<(int)((h->n_items + 127) / 128), 128, 0, h->stream>>>(h->Y, h->n_items, h->ks,
+                                                                        h->k, seed);
+  h->launches += 1;
+  CU(h, cudaGetLastError());
+  // a fresh build starts from an empty X (AlternatingLeastSquares.java:179)
+  CU(h, cudaMemsetAsync(h->X, 0, sizeof(float) * (size_t)h->users_alloc * h->ks, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return ALS_OK;
+}
+
+static int get_csr(als_handle* h, const Csr& c, int64_t* ptr, int32_t* idx, float* val) {
+  if (!h || !ptr || !idx || !val) return ALS_E_ARG;
+  if (!c.ptr) return fail(h, ALS_E_STATE, "interactions not set");
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaMemcpyAsync(ptr, c.ptr, sizeof(long long) * ((size_t)c.rows + 1), cudaMemcpyDeviceToHost,
+                        h->stream));
+  CU(h, cudaMemcpyAsync(idx, c.idx, sizeof(int) * (size_t)c.nnz, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(val, c.val, sizeof(float) * (size_t)c.nnz, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return ALS_OK;
+}
+int als_get_interactions(als_handle* h, int64_t* row_ptr, int32_t* col_idx, float* val) {
+  return h ? get_csr(h, h->by_user, row_ptr, col_idx, val) : ALS_E_ARG;
+}
+int als_get_interactions_by_column(als_handle* h, int64_t* col_ptr, int32_t* row_idx, float* val) {
+  if (!h) return ALS_E_ARG;
+  if (!h->have_by_item) return fail(h, ALS_E_STATE, "by-column orientation not built");
+  return get_csr(h, h->by_item, col_ptr, row_idx, val);
+}
+
+int als_get_interaction_rows(als_handle* h, int32_t by_column, int64_t first_row, int64_t n_rows,
+                             int64_t* row_ptr_out, int32_t* idx_out, float* val_out,
+                             int64_t capacity) {
+  if (!h || !row_ptr_out || n_rows < 0 || first_row < 0 || capacity < 0) return ALS_E_ARG;
+  const Csr& c = by_column ? h->by_item : h->by_user;
+  if (!c.ptr || (by_column && !h->have_by_item)) return fail(h, ALS_E_STATE, "interactions not set");
+  if (first_row + n_rows > c.rows) return fail(h, ALS_E_ARG, "row slice out of range");
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaMemcpyAsync(row_ptr_out, c.ptr + first_row, sizeof(long long) * ((size_t)n_rows + 1),
+                        cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  const long long e0 = row_ptr_out[0], e1 = row_ptr_out[n_rows];
+  if (e1 - e0 > capacity) return fail(h, ALS_E_ARG, "slice has %lld entries > capacity", e1 - e0);
+  for (long long r = 0; r <= n_rows; r++) row_ptr_out[r] -= e0;
+  if (e1 > e0) {
+    if (!idx_out || !val_out) return ALS_E_ARG;
+    CU(h, cudaMemcpyAsync(idx_out, c.idx + e0, sizeof(int) * (size_t)(e1 - e0),
+                          cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(val_out, c.val + e0, sizeof(float) * (size_t)(e1 - e0),
+                          cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
+  return ALS_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------
+int als_comm_unique_id_size(void) { return (int)sizeof(ncclUniqueId); }
+
+int als_comm_get_unique_id(void* out_id) {
+  if (!out_id) return ALS_E_ARG;
+  if (!load_nccl()) return ALS_E_NCCL;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return ALS_E_NCCL;
+  memcpy(out_id, &id, sizeof(id));
+  return ALS_OK;
+}
+
+int als_comm_init(als_handle* h, int32_t rank, int32_t world_size, const void* unique_id) {
+  if (!h || !unique_id || world_size < 1 || rank < 0 || rank >= world_size) return ALS_E_ARG;
+  if (h->by_user.ptr) return fail(h, ALS_E_STATE, "als_comm_init must precede als_set_interactions");
+  if (!load_nccl()) return fail(h, ALS_E_NCCL, "libnccl.so.2 not found");
+  CU(h, cudaSetDevice(h->device));
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof(id));
+  ncclResult_t r = g_nccl.CommInitRank(&h->comm, world_size, id, rank);
+  if (r != ncclSuccess) return fail(h, ALS_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+  h->rank = rank;
+  h->world = world_size;
+  return ALS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+// aux_kernels.cuh -- everything around the two hot kernels: CSR transposition
+// (RbyRow -> RbyColumn), the convergence probe, the synthetic workload generator
+// and the rare-path apparent-rank estimate.
+#pragma once
+#include <math.h>
+
+#include "common.cuh"
+
+namespace als {
+
+// ---------------------------------------------------------------------------
+// CSR -> (key=column, value=row<<32|valbits) expansion for the stable radix sort.
+__global__ void expand_rows_kernel(const long long* __restrict__ row_ptr, long long n_rows,
+                                   const int* __restrict__ col_idx, const float* __restrict__ val,
+                                   int* __restrict__ keys, unsigned long long* __restrict__ packed) {
+  // one warp per row: coalesced over the row's entries
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+  const int lane = threadIdx.x % kWarp;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) / kWarp;
+  for (long long r = warp; r < n_rows; r += n_warps) {
+    const long long e0 = row_ptr[r], e1 = row_ptr[r + 1];
+    for (long long e = e0 + lane; e < e1; e += kWarp) {
+      keys[e] = col_idx[e];
+      packed[e] = ((unsigned long long)(unsigned int)r << 32) |
+                  (unsigned long long)__float_as_uint(val[e]);
+    }
+  }
+}
+
+// Sorted keys -> col_ptr (col_ptr[c] = first position with key >= c), and unpack.
+__global__ void build_ptr_unpack_kernel(const int* __restrict__ keys_sorted,
+                                        const unsigned long long* __restrict__ packed_sorted,
+                                        long long nnz, long long n_cols,
+                                        long long* __restrict__ col_ptr, int* __restrict__ row_idx,
+                                        float* __restrict__ val) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+    const int kcur = keys_sorted[e];
+    const int kprev = (e == 0) ? -1 : keys_sorted[e - 1];
+    for (int c = kprev + 1; c <= kcur; c++) col_ptr[c] = e;
+    if (e == nnz - 1)
+      for (long long c = (long long)kcur + 1; c <= n_cols; c++) col_ptr[c] = nnz;
+    const unsigned long long pk = packed_sorted[e];
+    row_idx[e] = (int)(pk >> 32);
+    val[e] = __uint_as_float((unsigned int)(pk & 0xffffffffULL));
+  }
+}
+
+__global__ void fill_ptr_zero_kernel(long long* ptr, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ptr[i] = 0;
+}
+
+// ---------------------------------------------------------------------------
+// Convergence probe: out[i*ni+j] = dot(X[users[i]], Y[items[j]]), fp32-rounded
+// products summed in fp64 in index order (SimpleVectorMath.java:34-41).
+__global__ void probe_kernel(const float* __restrict__ X, const float* __restrict__ Y, int ks, int k,
+                             const int* __restrict__ users, int nu, const int* __restrict__ items,
+                             int ni, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nu * ni) return;
+  const float* x = X + (long long)users[t / ni] * ks;
+  const float* y = Y + (long long)items[t % ni] * ks;
+  double dot = 0.0;
+  for (int f = 0; f < k; f++) dot += (double)__fmul_rn(x[f], y[f]);
+  out[t] = dot;
+}
+
+// ---------------------------------------------------------------------------
+// Synthetic workload. Counter-based: value = f(seed,row,j), so any
+// shard is reproducible without host materialisation. tests/synth_ref.py holds the
+// numpy twin of these hashes.
+__host__ __device__ inline unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;
+  x ^= x >> 27; x *= 0x94D049BB133111EBULL;
+  x ^= x >> 31;
+  return x;
+}
+__host__ __device__ inline unsigned long long synth_hash(unsigned long long seed,
+                                                         unsigned long long row,
+                                                         unsigned long long j) {
+  return mix64(seed + row * 0x9E3779B97F4A7C15ULL + (j + 1ULL) * 0xD1B54A32D192ED03ULL);
+}
+
+// Each user draws nnz_per_user DISTINCT items: one uniformly from each of
+// nnz_per_user equal strata of [0,n_items) (distinct and ascending by construction);
+// strength uniform in {1..5}; negated with probability neg_fraction.
+__global__ void synth_rows_kernel(long long row_begin, long long n_local_rows, long long n_items,
+                                  int nnz_per_user, unsigned long long seed,
+                                  unsigned int neg_threshold_24, long long* __restrict__ row_ptr,
+                                  int* __restrict__ col_idx, float* __restrict__ val) {
+  const long long total = n_local_rows * nnz_per_user;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long r = e / nnz_per_user;
+    const int j = (int)(e % nnz_per_user);
+    const unsigned long long h = synth_hash(seed, (unsigned long long)(row_begin + r),
+                                            (unsigned long long)j);
+    const long long lo = ((long long)j * n_items) / nnz_per_user;
+    const long long hi = ((long long)(j + 1) * n_items) / nnz_per_user;
+    col_idx[e] = (int)(lo + (long long)((h >> 32) % (unsigned long long)(hi - lo)));
+    float s = (float)(1 + (int)((h & 0xffffULL) % 5ULL));
+    if (((h >> 8) & 0xffffffULL) < neg_threshold_24) s = -s;
+    val[e] = s;
+    if (j == 0) row_ptr[r] = r * (long long)nnz_per_user;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) row_ptr[n_local_rows] = total;
+}
+
+// Y0 rows: k i.i.d. N(0,1) (Box-Muller on hashed uniforms) normalised to unit L2.
+__global__ void synth_y0_kernel(float* __restrict__ Y, long long n_rows, int ks, int k,
+                                unsigned long long seed) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  float* y = Y + r * ks;
+  double total = 0.0;
+  for (int f = 0; f < k; f += 2) {
+    const unsigned long long h = synth_hash(seed ^ 0x5bf03635f0a5b2d1ULL, (unsigned long long)r,
+                                            (unsigned long long)f);
+    const float u1 = ((float)((h >> 40) & 0xffffffULL) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
+    const float u2 = (float)((h >> 8) & 0xffffffULL) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincosf(6.283185307179586f * u2, &s, &c);
+    const float g0 = rad * c, g1 = rad * s;
+    y[f] = g0;
+    total += (double)g0 * g0;
+    if (f + 1 < k) {
+      y[f + 1] = g1;
+      total += (double)g1 * g1;
+    }
+  }
+  const float norm = (float)sqrt(total);
+  for (int f = 0; f < k; f++) y[f] /= norm;  // SimpleVectorMath.normalize, :78-83
+  for (int f = k; f < ks; f++) y[f] = 0.f;
+}
+
+// ---------------------------------------------------------------------------
+// Rare path: apparent rank of the W_u that failed, for SingularMatrixSolverException
+// (CommonsMathLinearSystemSolver.java:46-54: new RRQRDecomposition(W,1e-5).getRank(0.01)).
+// One thread, fp64, W_u rebuilt exactly as Worker.call does. scratch: 2*k*k + 2k + 1 doubles.
+__global__ void singular_rank_kernel(const long long* row_ptr, const int* col_idx, const float* val,
+                                     long long local_row, const float* M, const double* G, int ks,
+                                     int k, double alpha, double lambda_alpha, int reconstruct_r,
+                                     int loss_ignores_unspecified, double* scratch, int* rank_out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double* W = scratch;            // row-major k x k
+  double* Q = scratch + k * k;    // qrt[col][row]
+  double* rDiag = Q + k * k;
+  const long long e0 = row_ptr[local_row], e1 = row_ptr[local_row + 1];
+  for (int i = 0; i < k; i++)
+    for (int j = 0; j < k; j++) W[i * k + j] = loss_ignores_unspecified ? 0.0 : G[i * ks + j];
+  for (long long e = e0; e < e1; e++) {
+    const float* y = M + (long long)col_idx[e] * ks;
+    const double w = (reconstruct_r ? 0.0 : alpha * fabs((double)val[e])) +
+                     (loss_ignores_unspecified ? 1.0 : 0.0);
+    for (int i = 0; i < k; i++)
+      for (int j = 0; j < k; j++) W[i * k + j] += ((double)y[i] * w) * (double)y[j];
+  }
+  for (int i = 0; i < k; i++) W[i * k + i] += lambda_alpha * (double)(e1 - e0);
+  // Householder QR with column pivoting on the transposed copy (commons-math3 3.2 RRQR).
+  for (int c = 0; c < k; c++)
+    for (int r = 0; r < k; r++) Q[c * k + r] = W[r * k + c];
+  for (int minor = 0; minor < k; minor++) {
+    double best = 0.0;
+    int besti = minor;
+    for (int i = minor; i < k; i++) {
+      double n2 = 0.0;
+      for (int j = 0; j < k; j++) n2 += Q[i * k + j] * Q[i * k + j];
+      if (n2 > best) { best = n2; besti = i; }
+    }
+    if (besti != minor)
+      for (int j = 0; j < k; j++) {
+        const double t = Q[minor * k + j];
+        Q[minor * k + j] = Q[besti * k + j];
+        Q[besti * k + j] = t;
+      }
+    double* qm = Q + minor * k;
+    double xNormSqr = 0.0;
+    for (int row = minor; row < k; row++) xNormSqr += qm[row] * qm[row];
+    const double a = (qm[minor] > 0) ? -sqrt(xNormSqr) : sqrt(xNormSqr);
+    rDiag[minor] = a;
+    if (a != 0.0) {
+      qm[minor] -= a;
+      for (int col = minor + 1; col < k; col++) {
+        double* qc = Q + col * k;
+        double al = 0.0;
+        for (int row = minor; row < k; row++) al -= qc[row] * qm[row];
+        al /= a * qm[minor];
+        for (int row = minor; row < k; row++) qc[row] -= al * qm[row];
+      }
+    }
+  }
+  // getRank(0.01): Frobenius norms of trailing blocks of R.
+  double* sq = rDiag + k;  // sq[s] = ||R[s:,s:]||_F^2, k+1 entries
+  sq[k] = 0.0;
+  for (int s = k - 1; s >= 0; s--) {
+    double acc = rDiag[s] * rDiag[s];
+    for (int col = s + 1; col < k; col++) acc += Q[col * k + s] * Q[col * k + s];
+    sq[s] = sq[s + 1] + acc;
+  }
+  int rank = 1;
+  double lastNorm = sqrt(sq[0]);
+  const double rNorm = lastNorm;
+  while (rank < k) {
+    const double thisNorm = sqrt(sq[rank]);
+    if (thisNorm == 0 || (thisNorm / lastNorm) * rNorm < 0.01) break;
+    lastNorm = thisNorm;
+    rank++;
+  }
+  *rank_out = rank;
+}
+
+}  // namespace als

@@ -1,0 +1,229 @@
+// row_update_simt.cuh -- CUDA-core row update: any feature count up to 128.
+//
+// One CTA per row of R (persistent grid, atomic row ticket).  Replaces the body of
+// Worker.call (AlternatingLeastSquares.java:438-502):
+//     W_u = G + sum_i alpha*|r_ui| * y_i y_i^T + lambda*alpha*n_u * I
+//     b_u = sum_{r_ui > 0} (1 + alpha*|r_ui|) * y_i
+//     x_u = W_u^{-1} b_u
+// The reference solves with a pivoted Householder QR in fp64
+// (CommonsMathLinearSystemSolver.java:41-45).  W_u is symmetric positive definite
+// whenever lambda*alpha*n_u > 0, so an LDL^T factorisation gives the same x_u; a
+// pivot <= the singularity threshold (or non-finite) reports ALS_E_SINGULAR instead
+// of emitting NaN/Inf (LinearSystemSolver.java:33-34 semantics).
+//
+// Data movement per row: n_u gathered factor rows of 4*KS bytes (coalesced float4,
+// staged in shared memory), n_u (index,value) pairs streamed, one 4*KS-byte row
+// written.  Arithmetic: lower-triangular 4x4 register tiles, packed fp32x2 FMAs.
+#pragma once
+#include "common.cuh"
+
+namespace als {
+
+struct RowUpdateParams {
+  const long long* row_ptr;  // CSR of this orientation, local rows [0, n_rows]
+  const int* col_idx;
+  const float* val;
+  long long n_rows;      // local rows to process
+  long long row_offset;  // global index of local row 0 in `out`
+  const float* M;        // opposite factor, [n_other][KS]
+  const double* G;       // M^T M, [KS*KS] fp64
+  float* out;            // this factor, [n][KS]; padding columns stay 0
+  int k;                 // true feature count (<= KS)
+  float alpha;
+  double lambda_alpha;   // lambda * alpha  (AlternatingLeastSquares.java:435)
+  int reconstruct_r;
+  int loss_ignores_unspecified;
+  float threshold;
+  int which;  // 0 = X half, 1 = Y half (for error reports)
+  DeviceStatus* status;
+  unsigned long long* ticket;  // zeroed before launch
+};
+
+constexpr int kSimtThreads = 128;
+constexpr int kSimtChunk = 32;  // gathered rows staged per step
+
+template <int KS>
+struct SimtShape {
+  static constexpr int T = KS / 4;
+  static constexpr int NTL = T * (T + 1) / 2;  // lower-triangular 4x4 tiles
+  static constexpr int TPT = (NTL + kSimtThreads - 1) / kSimtThreads;
+  static constexpr int LDW = KS + 1;  // padded leading dimension of W in smem
+  static constexpr size_t smem_bytes() {
+    return sizeof(float) * ((size_t)KS * LDW + (size_t)kSimtChunk * KS + 2 * kSimtChunk + 3 * KS) +
+           sizeof(int) * kSimtChunk + 16;
+  }
+};
+
+template <int KS>
+__global__ void __launch_bounds__(kSimtThreads)
+row_update_simt_kernel(const RowUpdateParams p) {
+  using S = SimtShape<KS>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* Ys = reinterpret_cast<float*>(smem_raw);  // [chunk][KS], 16B aligned
+  float* W = Ys + kSimtChunk * KS;                 // [KS][LDW]
+  float* wgt = W + KS * S::LDW;                    // [chunk] SYRK weight
+  float* cb = wgt + kSimtChunk;                    // [chunk] rhs weight
+  float* bvec = cb + kSimtChunk;                   // [KS]
+  float* invd = bvec + KS;                         // [KS]
+  float* xs = invd + KS;                           // [KS]
+  int* idx = reinterpret_cast<int*>(xs + KS);      // [chunk]
+  __shared__ long long s_row;
+  __shared__ int s_fail;
+
+  const int tid = threadIdx.x;
+  const int k = p.k;
+
+  // tile coordinates of this thread's lower-triangular tiles
+  int ti[S::TPT], tj[S::TPT];
+#pragma unroll
+  for (int t = 0; t < S::TPT; t++) {
+    const int tile = tid + t * kSimtThreads;
+    int i = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= tile) i++;
+    while (i * (i + 1) / 2 > tile) i--;
+    ti[t] = i;
+    tj[t] = tile - i * (i + 1) / 2;
+    if (tile >= S::NTL) { ti[t] = -1; tj[t] = 0; }
+  }
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      s_row = (long long)atomicAdd(p.ticket, 1ULL);
+      s_fail = 0;
+    }
+    __syncthreads();
+    const long long row = s_row;
+    if (row >= p.n_rows) break;
+    const long long e0 = p.row_ptr[row], e1 = p.row_ptr[row + 1];
+    const long long nu = e1 - e0;
+    if (nu == 0) continue;  // not in the reference's map: leave the factor row untouched
+
+    float2 acc[S::TPT][8];
+#pragma unroll
+    for (int t = 0; t < S::TPT; t++)
+#pragma unroll
+      for (int e = 0; e < 8; e++) acc[t][e] = make_float2(0.f, 0.f);
+    float bacc = 0.f;
+
+    for (long long c0 = e0; c0 < e1; c0 += kSimtChunk) {
+      const int n = (int)min((long long)kSimtChunk, e1 - c0);
+      __syncthreads();  // previous chunk fully consumed
+      if (tid < n) {
+        const int ci = ld_stream_i32(p.col_idx + c0 + tid);
+        const float r = ld_stream_f32(p.val + c0 + tid);
+        idx[tid] = ci;
+        const float ar = p.alpha * fabsf(r);
+        // SYRK weight: (c_u - 1) = alpha*|r| (ALS.java:471-479); +1 when the loss ignores
+        // unspecified entries (partialTransposeTimesSelf, :524-539); 0 when reconstructing R.
+        wgt[tid] = (p.reconstruct_r ? 0.f : ar) + (p.loss_ignores_unspecified ? 1.f : 0.f);
+        // rhs weight: r (ALS.java:466-469) or c_u gated on r > 0 (:480-482)
+        cb[tid] = p.reconstruct_r ? r : (r > 0.f ? 1.f + ar : 0.f);
+      }
+      __syncthreads();
+      constexpr int V = KS / 4;
+#pragma unroll 4
+      for (int i = tid; i < n * V; i += kSimtThreads) {
+        const int e = i / V, q = i % V;
+        const float4 v = ldg_f4(p.M + (long long)idx[e] * KS + 4 * q);
+        *reinterpret_cast<float4*>(Ys + e * KS + 4 * q) = v;
+      }
+      __syncthreads();
+      for (int e = 0; e < n; e++) {
+        const float w = wgt[e];
+#pragma unroll
+        for (int t = 0; t < S::TPT; t++) {
+          if (ti[t] < 0) continue;
+          const float4 a = *reinterpret_cast<const float4*>(Ys + e * KS + 4 * ti[t]);
+          const float4 b = *reinterpret_cast<const float4*>(Ys + e * KS + 4 * tj[t]);
+          const float2 b01 = make_float2(b.x, b.y), b23 = make_float2(b.z, b.w);
+          const float a0 = a.x * w, a1 = a.y * w, a2 = a.z * w, a3 = a.w * w;
+          acc[t][0] = ffma2(make_float2(a0, a0), b01, acc[t][0]);
+          acc[t][1] = ffma2(make_float2(a0, a0), b23, acc[t][1]);
+          acc[t][2] = ffma2(make_float2(a1, a1), b01, acc[t][2]);
+          acc[t][3] = ffma2(make_float2(a1, a1), b23, acc[t][3]);
+          acc[t][4] = ffma2(make_float2(a2, a2), b01, acc[t][4]);
+          acc[t][5] = ffma2(make_float2(a2, a2), b23, acc[t][5]);
+          acc[t][6] = ffma2(make_float2(a3, a3), b01, acc[t][6]);
+          acc[t][7] = ffma2(make_float2(a3, a3), b23, acc[t][7]);
+        }
+        if (tid < KS) bacc = fmaf(cb[e], Ys[e * KS + tid], bacc);
+      }
+    }
+
+    // W = G + acc (+ lambda*alpha*n_u on the diagonal); lower triangle only.
+    const bool add_g = !p.loss_ignores_unspecified;
+#pragma unroll
+    for (int t = 0; t < S::TPT; t++) {
+      if (ti[t] < 0) continue;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int r = 4 * ti[t] + i, c = 4 * tj[t] + j;
+          const float2 v2 = acc[t][2 * i + j / 2];
+          double v = (double)((j & 1) ? v2.y : v2.x);
+          if (add_g) v += p.G[r * KS + c];
+          if (r == c) v += p.lambda_alpha * (double)nu;
+          W[r * S::LDW + c] = (float)v;
+        }
+      }
+    }
+    if (tid < KS) bvec[tid] = bacc;
+
+    // LDL^T, right-looking, one barrier per column. Column j keeps the unscaled
+    // values W[i][j] = L[i][j]*d_j; invd[j] = 1/d_j.
+    const int tx = tid % 16, ty = tid / 16;
+    for (int j = 0; j < k; j++) {
+      __syncthreads();
+      const float d = W[j * S::LDW + j];
+      if (!(d > p.threshold) || !isfinite(d)) {
+        if (tid == 0) {
+          report_error(p.status, ALS_E_SINGULAR, p.which, p.row_offset + row, d);
+          s_fail = 1;
+        }
+        break;
+      }
+      const float id = 1.0f / d;
+      if (tid == 0) invd[j] = id;
+      for (int i = j + 1 + ty; i < k; i += kSimtThreads / 16) {
+        const float lij = W[i * S::LDW + j] * id;
+        for (int c = j + 1 + tx; c <= i; c += 16) {
+          W[i * S::LDW + c] = fmaf(-lij, W[c * S::LDW + j], W[i * S::LDW + c]);
+        }
+      }
+    }
+    __syncthreads();
+    if (s_fail) continue;
+
+    // Solve L D L^T x = b with warp 0 (k sequential steps each way).
+    if (tid < kWarp) {
+      // forward: z = L^{-1} b   (column oriented)
+      for (int j = 0; j < k; j++) {
+        const float t = bvec[j] * invd[j];
+        for (int i = j + 1 + tid; i < k; i += kWarp) bvec[i] = fmaf(-W[i * S::LDW + j], t, bvec[i]);
+        __syncwarp();
+      }
+      // y = D^{-1} z
+      for (int i = tid; i < k; i += kWarp) bvec[i] *= invd[i];
+      __syncwarp();
+      // backward: x = L^{-T} y   (row j of W holds L[j][i]*d_i)
+      for (int j = k - 1; j >= 0; j--) {
+        const float xj = bvec[j];
+        for (int i = tid; i < j; i += kWarp)
+          bvec[i] = fmaf(-W[j * S::LDW + i] * invd[i], xj, bvec[i]);
+        __syncwarp();
+      }
+      bool bad = false;
+      float* dst = p.out + (p.row_offset + row) * KS;
+      for (int i = tid; i < k; i += kWarp) {
+        const float x = bvec[i];
+        bad |= !isfinite(x);
+        dst[i] = x;
+      }
+      if (bad) report_error(p.status, ALS_E_NONFINITE, p.which, p.row_offset + row, 0.f);
+    }
+  }
+}
+
+}  // namespace als

@@ -1,0 +1,528 @@
+"""Host-side mirror of the reference's factorizer interface over the C ABI.
+
+  MatrixFactorizer          online/.../factorizer/MatrixFactorizer.java:31-77
+  AlternatingLeastSquares   online/.../factorizer/als/AlternatingLeastSquares.java:66-543
+
+Same names, argument meaning and error behaviour as the Java so the parity tests read
+like the reference's own (AlternatingLeastSquaresTest.java:39-117).  The maps at the
+boundary are plain dicts: FastByIDMap<FastByIDFloatMap> -> {long: {long: float}},
+FastByIDMap<float[]> -> {long: float32 ndarray}.  All arithmetic happens on the GPU
+through libmyrrix_als.so; this file only flattens IDs, owns the stop rule
+(ALS.java:227-257) and maps status codes back onto the reference's exceptions.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _native as N
+
+# JVM system properties the reference reads on this path, same names.
+properties = {}
+
+DEFAULT_FEATURES = 30                      # MatrixFactorizer.java:34
+DEFAULT_ALPHA = 1.0                        # AlternatingLeastSquares.java:71
+DEFAULT_LAMBDA = 0.1                       # :73
+DEFAULT_CONVERGENCE_THRESHOLD = 0.001      # :74
+DEFAULT_MAX_ITERATIONS = 30                # :75
+NUM_USER_ITEMS_TO_TEST_CONVERGENCE = 100   # :78
+
+
+class SolverException(RuntimeError):
+    """common/.../math/SolverException.java"""
+
+
+class SingularMatrixSolverException(SolverException):
+    """common/.../math/SingularMatrixSolverException.java:23-52 (unchecked, carries apparentRank)."""
+
+    def __init__(self, apparent_rank=0, message=""):
+        super().__init__(message)
+        self.apparent_rank = apparent_rank
+
+    def getApparentRank(self):
+        return self.apparent_rank
+
+
+class ExecutionException(RuntimeError):
+    """java.util.concurrent.ExecutionException stand-in for CUDA/NCCL/OOM failures."""
+
+
+def _prop_bool(name, default=False):
+    v = properties.get(name)
+    return default if v is None else str(v).lower() == "true"
+
+
+def _prop_float(name, default):
+    v = properties.get(name)
+    if v is None:
+        return default
+    f = float(v)
+    if not math.isfinite(f):  # LangUtils.parseDouble (common/.../LangUtils.java:60-64)
+        raise ValueError("Bad value: %s" % v)
+    return f
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class NativeALS:
+    """Thin RAII wrapper of one als_handle. Raises on every non-OK status."""
+
+    def __init__(self, features, alpha=DEFAULT_ALPHA, lam=DEFAULT_LAMBDA, reconstruct_r=False,
+                 loss_ignores_unspecified=False, singularity_threshold=1.0e-5, device=0,
+                 kernel=N.ALS_KERNEL_AUTO):
+        self.lib = N.load()
+        cfg = N.AlsConfig()
+        self.lib.als_config_default(C.byref(cfg))
+        cfg.features = int(features)
+        cfg.alpha = float(alpha)
+        cfg.lambda_ = float(lam)
+        cfg.reconstruct_r = int(bool(reconstruct_r))
+        cfg.loss_ignores_unspecified = int(bool(loss_ignores_unspecified))
+        cfg.singularity_threshold = float(singularity_threshold)
+        cfg.device = int(device)
+        cfg.kernel = int(kernel)
+        self.h = C.c_void_p()
+        self.features = int(features)
+        rc = self.lib.als_create(C.byref(cfg), C.byref(self.h))
+        if rc != N.ALS_OK:
+            msg = self.lib.als_last_error(self.h).decode() if self.h else ""
+            if self.h:
+                self.lib.als_destroy(self.h)
+                self.h = C.c_void_p()
+            if rc == N.ALS_E_ARG:
+                raise ValueError("als_create: invalid argument %s" % msg)
+            raise ExecutionException("als_create failed: %s %s" % (N.STATUS_NAMES[rc], msg))
+        self.n_users = self.n_items = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.als_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def check(self, rc):
+        if rc == N.ALS_OK:
+            return
+        msg = self.lib.als_last_error(self.h).decode()
+        if rc == N.ALS_E_SINGULAR:
+            raise SingularMatrixSolverException(self.lib.als_singular_rank(self.h), msg)
+        if rc == N.ALS_E_NONFINITE:
+            raise SolverException(msg)
+        if rc == N.ALS_E_ARG:
+            raise ValueError(msg)
+        raise ExecutionException("%s: %s" % (N.STATUS_NAMES[rc], msg))
+
+    # -- data ---------------------------------------------------------------
+    def set_interactions(self, n_users, n_items, row_ptr, col_idx, val, by_column=None):
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        col_idx = np.ascontiguousarray(col_idx, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float32)
+        if col_idx.size and (col_idx.min() < 0 or col_idx.max() >= n_items):
+            raise ValueError("column index out of range")
+        self.check(self.lib.als_set_interactions(
+            self.h, n_users, n_items, row_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+            col_idx.ctypes.data_as(C.POINTER(C.c_int32)), _fp(val)))
+        if by_column is not None:
+            cp, ri, cv = by_column
+            cp = np.ascontiguousarray(cp, dtype=np.int64)
+            ri = np.ascontiguousarray(ri, dtype=np.int32)
+            cv = np.ascontiguousarray(cv, dtype=np.float32)
+            self.check(self.lib.als_set_interactions_by_column(
+                self.h, cp.ctypes.data_as(C.POINTER(C.c_int64)),
+                ri.ctypes.data_as(C.POINTER(C.c_int32)), _fp(cv)))
+        self.n_users, self.n_items = int(n_users), int(n_items)
+
+    def set_interactions_device(self, n_users, n_items, d_row_ptr, d_col_idx, d_val):
+        self.check(self.lib.als_set_interactions_device(self.h, n_users, n_items, d_row_ptr,
+                                                        d_col_idx, d_val))
+        self.n_users, self.n_items = int(n_users), int(n_items)
+
+    def synth_interactions(self, n_users, n_items, nnz_per_user, seed=1234567890, neg_fraction=0.0):
+        self.check(self.lib.als_synth_interactions(self.h, n_users, n_items, nnz_per_user, seed,
+                                                   neg_fraction))
+        self.n_users, self.n_items = int(n_users), int(n_items)
+
+    def synth_y0(self, seed=1234567890):
+        self.check(self.lib.als_synth_y0(self.h, seed))
+
+    def set_y(self, y):
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        if y.shape != (self.n_items, self.features):
+            raise ValueError("Y must be n_items x features")
+        self.check(self.lib.als_set_y(self.h, _fp(y)))
+
+    def set_x(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.shape != (self.n_users, self.features):
+            raise ValueError("X must be n_users x features")
+        self.check(self.lib.als_set_x(self.h, _fp(x)))
+
+    def get_x(self, out=None):
+        if out is None:
+            out = np.empty((self.n_users, self.features), dtype=np.float32)
+        self.check(self.lib.als_get_x(self.h, _fp(out)))
+        return out
+
+    def get_y(self, out=None):
+        if out is None:
+            out = np.empty((self.n_items, self.features), dtype=np.float32)
+        self.check(self.lib.als_get_y(self.h, _fp(out)))
+        return out
+
+    def get_interactions(self, by_column=False):
+        info = self.info()
+        rows = self.n_items if by_column else self.n_users
+        ptr = np.empty(rows + 1, dtype=np.int64)
+        idx = np.empty(info.nnz, dtype=np.int32)
+        val = np.empty(info.nnz, dtype=np.float32)
+        fn = self.lib.als_get_interactions_by_column if by_column else self.lib.als_get_interactions
+        self.check(fn(self.h, ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                      idx.ctypes.data_as(C.POINTER(C.c_int32)), _fp(val)))
+        return ptr, idx, val
+
+    def get_interaction_rows(self, first_row, n_rows, by_column=False, capacity=None):
+        ptr = np.empty(n_rows + 1, dtype=np.int64)
+        if capacity is None:
+            capacity = self.info().nnz
+        idx = np.empty(capacity, dtype=np.int32)
+        val = np.empty(capacity, dtype=np.float32)
+        self.check(self.lib.als_get_interaction_rows(
+            self.h, int(by_column), first_row, n_rows, ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+            idx.ctypes.data_as(C.POINTER(C.c_int32)), _fp(val), capacity))
+        n = int(ptr[-1])
+        return ptr, idx[:n].copy(), val[:n].copy()
+
+    # -- compute ------------------------------------------------------------
+    def half_x(self):
+        self.check(self.lib.als_half_x(self.h))
+
+    def half_y(self):
+        self.check(self.lib.als_half_y(self.h))
+
+    def iterate(self, n):
+        self.check(self.lib.als_iterate(self.h, n))
+
+    def sync(self):
+        self.check(self.lib.als_sync(self.h))
+
+    def probe(self, users, items):
+        users = np.ascontiguousarray(users, dtype=np.int32)
+        items = np.ascontiguousarray(items, dtype=np.int32)
+        out = np.zeros((users.size, items.size), dtype=np.float64)
+        self.check(self.lib.als_probe(self.h, users.ctypes.data_as(C.POINTER(C.c_int32)), users.size,
+                                      items.ctypes.data_as(C.POINTER(C.c_int32)), items.size,
+                                      out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def gramian(self, which):
+        out = np.zeros((self.features, self.features), dtype=np.float64)
+        self.check(self.lib.als_gramian(self.h, 0 if which in (0, "x", "X") else 1,
+                                        out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def set_stream(self, cuda_stream):
+        self.check(self.lib.als_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def info(self):
+        info = N.AlsInfo()
+        self.check(self.lib.als_get_info(self.h, C.byref(info)))
+        return info
+
+    def profile(self, on=True):
+        self.check(self.lib.als_profile_enable(self.h, int(on)))
+
+    def timings(self, reset=False):
+        t = N.AlsTimings()
+        self.check(self.lib.als_get_timings(self.h, C.byref(t), int(reset)))
+        return t
+
+    def comm_init(self, rank, world_size, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), len(unique_id))
+        self.check(self.lib.als_comm_init(self.h, rank, world_size, buf))
+
+
+def comm_unique_id():
+    lib = N.load()
+    n = lib.als_comm_unique_id_size()
+    buf = C.create_string_buffer(n)
+    rc = lib.als_comm_get_unique_id(buf)
+    if rc != N.ALS_OK:
+        raise ExecutionException("als_comm_get_unique_id: %s" % N.STATUS_NAMES[rc])
+    return buf.raw
+
+
+class DoubleWeightedMean:
+    """common/.../stats/DoubleWeightedMean.java:33-101 (increment only)."""
+
+    def __init__(self):
+        self.totalWeight = 0.0
+        self.mean = float("nan")
+
+    def increment(self, datum, weight=1.0):
+        old = self.totalWeight
+        self.totalWeight += weight
+        if old <= 0:
+            self.mean = datum
+        else:
+            self.mean = self.mean * old / self.totalWeight + datum * weight / self.totalWeight
+
+    def getResult(self):
+        return self.mean
+
+
+class MatrixFactorizer:
+    """online/.../factorizer/MatrixFactorizer.java:31-77"""
+    DEFAULT_FEATURES = DEFAULT_FEATURES
+
+    def call(self):
+        raise NotImplementedError
+
+    def setPreviousX(self, previousX):
+        raise NotImplementedError
+
+    def setPreviousY(self, previousY):
+        raise NotImplementedError
+
+    def getX(self):
+        raise NotImplementedError
+
+    def getY(self):
+        raise NotImplementedError
+
+
+class AlternatingLeastSquares(MatrixFactorizer):
+    """Drop-in for net.myrrix.online.factorizer.als.AlternatingLeastSquares.
+
+    `RbyRow` / `RbyColumn`: {userID: {itemID: strength}} / {itemID: {userID: strength}}
+    (FastByIDMap<FastByIDFloatMap>, ctor at AlternatingLeastSquares.java:132-147).
+    """
+
+    def __init__(self, RbyRow, RbyColumn, features=DEFAULT_FEATURES,
+                 estimateErrorConvergenceThreshold=DEFAULT_CONVERGENCE_THRESHOLD,
+                 maxIterations=DEFAULT_MAX_ITERATIONS, device=0, kernel=N.ALS_KERNEL_AUTO,
+                 random=None):
+        # Preconditions, ALS.java:137-141
+        if RbyRow is None or RbyColumn is None:
+            raise TypeError("RbyRow/RbyColumn must not be null")
+        if not features > 0:
+            raise ValueError("features must be positive: %s" % features)
+        if not (0.0 < estimateErrorConvergenceThreshold < 1.0):
+            raise ValueError("threshold must be in (0,1): %s" % estimateErrorConvergenceThreshold)
+        self.RbyRow = RbyRow
+        self.RbyColumn = RbyColumn
+        self.features = int(features)
+        self.estimateErrorConvergenceThreshold = float(estimateErrorConvergenceThreshold)
+        self.maxIterations = int(maxIterations)
+        self.X = None
+        self.Y = None
+        self.previousY = None
+        self.device = device
+        self.kernel = kernel
+        self.random = random if random is not None else np.random.default_rng(1234567890)
+        self.iterationsRun = 0
+        self.lastConvergenceValue = float("nan")
+
+    def getX(self):
+        return self.X
+
+    def getY(self):
+        return self.Y
+
+    def setPreviousX(self, previousX):
+        pass  # "Does nothing." ALS.java:162-165
+
+    def setPreviousY(self, previousY):
+        self.previousY = previousY
+
+    # -- constructInitialY, ALS.java:264-335 ---------------------------------
+    def _random_unit_vector(self):
+        # RandomUtils.doRandomUnitVector (common/.../random/RandomUtils.java:88-100)
+        d = self.random.standard_normal(self.features)
+        v = d.astype(np.float32)
+        v /= np.float32(math.sqrt(float(np.dot(d, d))))
+        return v
+
+    def _random_unit_vector_far_from(self, far_from):
+        # RandomUtils.randomUnitVectorFarFrom (RandomUtils.java:110-140); the RNG stream is
+        # numpy's, not MersenneTwister's, so cold starts are statistically -- not bitwise --
+        # the reference's.
+        size = len(far_from)
+        num_samples = min(100, size)
+        while True:
+            v = self._random_unit_vector()
+            smallest = float("inf")
+            for s in range(num_samples):
+                other = far_from[s if size == num_samples else int(self.random.integers(size))]
+                dist2 = 2.0 - 2.0 * float(np.dot(v.astype(np.float64), other.astype(np.float64)))
+                if math.isfinite(dist2) and dist2 < smallest:
+                    smallest = dist2
+            if math.isfinite(smallest) and not (self.features == 1 and smallest == 0.0):
+                if self.random.random() < smallest / 4.0:
+                    return v
+            else:
+                return v
+
+    def _construct_initial_y(self, previousY):
+        k = self.features
+        if not previousY:
+            randomY = {}
+        else:
+            old = len(next(iter(previousY.values())))
+            if old > k:  # ALS.java:277-287
+                randomY = {}
+                for key, vec in previousY.items():
+                    v = np.array(vec[:k], dtype=np.float32)
+                    v /= np.float32(math.sqrt(float(np.sum(v.astype(np.float64) ** 2))))
+                    randomY[key] = v
+            elif old < k:  # ALS.java:289-302
+                randomY = {}
+                for key, vec in previousY.items():
+                    v = np.zeros(k, dtype=np.float32)
+                    v[:old] = vec
+                    v[old:] = self.random.standard_normal(k - old).astype(np.float32)
+                    v /= np.float32(math.sqrt(float(np.sum(v.astype(np.float64) ** 2))))
+                    randomY[key] = v
+            else:  # adopt in place, ALS.java:304-308
+                randomY = previousY
+        recent = []
+        for vec in randomY.values():
+            if len(recent) >= 100000:
+                break
+            recent.append(np.asarray(vec, dtype=np.float32))
+        for item_id in self.RbyColumn.keys():
+            if item_id not in randomY:
+                v = self._random_unit_vector_far_from(recent)
+                randomY[item_id] = v
+                if len(recent) < 100000:
+                    recent.append(v)
+        return randomY
+
+    # -- flattening: long IDs -> dense indices, maps -> CSR --------------------
+    @staticmethod
+    def _flatten(R, row_index, col_index):
+        n_rows = len(row_index)
+        counts = np.zeros(n_rows + 1, dtype=np.int64)
+        for rid, row in R.items():
+            counts[row_index[rid] + 1] = len(row)
+        ptr = np.cumsum(counts)
+        idx = np.empty(int(ptr[-1]), dtype=np.int32)
+        val = np.empty(int(ptr[-1]), dtype=np.float32)
+        for rid, row in R.items():
+            o = int(ptr[row_index[rid]])
+            for j, (cid, v) in enumerate(row.items()):
+                idx[o + j] = col_index[cid]
+                val[o + j] = v
+        return ptr, idx, val
+
+    def _choose_about_n(self, keys, n):
+        # RandomUtils.chooseAboutNFromStream (RandomUtils.java:202-217)
+        keys = list(keys)
+        if n < len(keys):
+            rate = float(n) / len(keys)
+            keys = [key for key in keys if self.random.random() < rate]
+        return keys
+
+    def call(self):
+        k = self.features
+        randomY = not self.previousY  # ALS.java:181
+        Ymap = self._construct_initial_y(self.previousY)
+        user_ids = list(self.RbyRow.keys())
+        # every row of Y counts in Y^T Y, including stale rows absent from RbyColumn
+        item_ids = list(Ymap.keys())
+        uindex = {u: i for i, u in enumerate(user_ids)}
+        iindex = {it: i for i, it in enumerate(item_ids)}
+        for it in self.RbyColumn.keys():
+            if it not in iindex:  # cannot happen after constructInitialY; keep the invariant explicit
+                raise AssertionError("item without a Y row")
+        r_ptr, r_idx, r_val = self._flatten(self.RbyRow, uindex, iindex)
+        c_full = {it: self.RbyColumn.get(it, {}) for it in item_ids}
+        c_ptr, c_idx, c_val = self._flatten(c_full, iindex, uindex)
+        if r_ptr[-1] != c_ptr[-1]:
+            raise ValueError("RbyRow and RbyColumn disagree")
+
+        alpha = _prop_float("model.als.alpha", DEFAULT_ALPHA)
+        lam = _prop_float("model.als.lambda", DEFAULT_LAMBDA)
+        als = NativeALS(k, alpha=alpha, lam=lam,
+                        reconstruct_r=_prop_bool("model.reconstructRMatrix"),
+                        loss_ignores_unspecified=_prop_bool("model.lossIgnoresUnspecified"),
+                        singularity_threshold=_prop_float("common.matrix.singularityThreshold", 1e-5),
+                        device=self.device, kernel=self.kernel)
+        try:
+            n_users, n_items = len(user_ids), len(item_ids)
+            if n_users == 0 or n_items == 0:
+                self.X, self.Y = {}, dict(Ymap)
+                return None
+            als.set_interactions(n_users, n_items, r_ptr, r_idx, r_val, by_column=(c_ptr, c_idx, c_val))
+            Y0 = np.stack([np.asarray(Ymap[it], dtype=np.float32) for it in item_ids])
+            als.set_y(Y0)
+
+            def publish():
+                Xd, Yd = als.get_x(), als.get_y()
+                # rows present in RbyRow with no entries solve to 0 (W=G, b=0)
+                self.X = {u: Xd[i].copy() for i, u in enumerate(user_ids)}
+                newY = {}
+                for i, it in enumerate(item_ids):
+                    row = c_full[it]
+                    if it in self.RbyColumn and len(row) == 0:
+                        newY[it] = np.zeros(k, dtype=np.float32)
+                    else:
+                        newY[it] = Yd[i].copy()
+                if Ymap is self.previousY:  # adopted in place (ALS.java:304-308)
+                    for it, v in newY.items():
+                        Ymap[it] = v
+                    self.Y = Ymap
+                else:
+                    self.Y = newY
+
+            if not _prop_bool("model.als.iterate", True):  # ALS.java:196-204
+                als.half_x()
+                als.sync()
+                publish()
+                return None
+
+            present_items = [it for it in self.RbyColumn.keys()]
+            test_users = self._choose_about_n(user_ids, NUM_USER_ITEMS_TO_TEST_CONVERGENCE)
+            test_items = self._choose_about_n(present_items, NUM_USER_ITEMS_TO_TEST_CONVERGENCE)
+            tu = np.array([uindex[u] for u in test_users], dtype=np.int32)
+            ti = np.array([iindex[it] for it in test_items], dtype=np.int32)
+            estimates = np.zeros((tu.size, ti.size), dtype=np.float64)  # X empty: stay 0 (:215-223)
+
+            iterationNumber = 0
+            while True:
+                als.half_x()   # iterateXFromY, :228
+                als.half_y()   # iterateYFromX, :229
+                als.sync()     # surfaces SingularMatrixSolverException like Future.get() (:349)
+                new = als.probe(tu, ti)
+                mean = DoubleWeightedMean()
+                for i in range(tu.size):
+                    for j in range(ti.size):
+                        nv = float(new[i, j])
+                        mean.increment(abs(nv - estimates[i, j]), max(0.0, nv))
+                estimates = new
+                iterationNumber += 1
+                self.iterationsRun = iterationNumber
+                if self.maxIterations > 0 and iterationNumber >= self.maxIterations:
+                    break
+                conv = mean.getResult()
+                self.lastConvergenceValue = conv
+                if not math.isfinite(conv):
+                    break
+                if not (randomY and iterationNumber == 1) and conv < self.estimateErrorConvergenceThreshold:
+                    break
+            publish()
+        finally:
+            als.close()
+        return None

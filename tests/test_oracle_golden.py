@@ -1,0 +1,121 @@
+"""Pins the CPU oracle (oracle/als_oracle.c) against every golden vector the reference's own
+tests hold for the ALS path (tests/golden/make_golden.py lists file:line for each)."""
+import numpy as np
+import pytest
+
+from conftest import dense_to_csr
+from oracle import oracle as O
+
+
+def _product(X, Y):
+    # MatrixUtils.multiplyXYT (MatrixUtils.java:153-163) -> SimpleVectorMath.dot
+    return np.array([[O.dot(x, y) for y in Y] for x in X])
+
+
+def test_als_golden(goldens):
+    """AlternatingLeastSquaresTest.testALS (:39-57): 25 entries of X*Y^T to 1e-6."""
+    g = goldens["als"]
+    ptr, idx, val = dense_to_csr(g["R"])
+    X, Y, its, conv = O.als_run(ptr, idx, val, 5, np.array(g["Y0"], np.float32),
+                                convergence_threshold=g["threshold"],
+                                max_iterations=g["max_iterations"])
+    assert np.abs(_product(X, Y) - np.array(g["product"])).max() < goldens["float_epsilon"]
+    assert its == 28 and conv < g["threshold"]
+
+
+def test_als_golden_reconstruct_r(goldens):
+    """AlternatingLeastSquaresTest.testALSPredictingR (:60-78), model.reconstructRMatrix=true."""
+    g = goldens["als"]
+    ptr, idx, val = dense_to_csr(g["R"])
+    X, Y, its, _ = O.als_run(ptr, idx, val, 5, np.array(g["Y0"], np.float32),
+                             convergence_threshold=g["threshold"],
+                             max_iterations=g["max_iterations"], reconstruct_r=True)
+    assert np.abs(_product(X, Y) - np.array(g["product_reconstruct_r"])).max() < goldens["float_epsilon"]
+    assert its == 34
+
+
+def test_negative_input_golden(goldens):
+    """NegativeInputTest.testALS (:37-80): negative strengths feed W but not b."""
+    g = goldens["negative_input"]
+    ptr, idx, val = dense_to_csr(g["R"])
+    X, Y, its, _ = O.als_run(ptr, idx, val, 4, np.array(g["Y0"], np.float32),
+                             convergence_threshold=g["threshold"],
+                             max_iterations=g["max_iterations"])
+    assert np.abs(_product(X, Y) - np.array(g["product"])).max() < goldens["float_epsilon"]
+    assert its == 19
+
+
+def test_transpose_times_self_golden(goldens):
+    """MatrixUtilsTest.testTransposeTimesSelf (:63-73), exact to 1e-12."""
+    g = goldens["transpose_times_self"]
+    G = O.transpose_times_self(np.array(g["M"], np.float32))
+    assert np.abs(G - np.array(g["MTM"])).max() <= goldens["double_epsilon"]
+
+
+def test_simple_vector_math_golden(goldens):
+    """SimpleVectorMathTest (:29-37)."""
+    g = goldens["simple_vector_math"]
+    assert abs(O.dot(g["vec1"], g["vec2"]) - g["dot"]) <= goldens["double_epsilon"]
+    assert abs(O.norm(g["vec1"]) - g["norm1"]) <= goldens["double_epsilon"]
+    assert abs(O.norm(g["vec2"]) - g["norm2"]) <= goldens["double_epsilon"]
+
+
+def test_transpose_times_self_rounds_products_to_fp32():
+    """MatrixUtils.java:231-233: float*float is rounded to fp32 before the fp64 add."""
+    M = np.array([[1.0000001, 3.0000002]], np.float32)
+    G = O.transpose_times_self(M)
+    assert G[0, 1] == float(np.float32(M[0, 0] * M[0, 1]))
+    assert G[0, 1] != float(M[0, 0]) * float(M[0, 1])
+
+
+def test_solver_matches_numpy():
+    rng = np.random.default_rng(0)
+    for k in (1, 2, 7, 30, 64):
+        A = rng.standard_normal((k + 5, k))
+        W = A.T @ A + 0.3 * np.eye(k)
+        b = rng.standard_normal(k)
+        x = O.solve(W, b)
+        ref = np.linalg.solve(W, b)
+        assert np.abs(x - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+
+
+def test_solver_singular_reports_rank():
+    """CommonsMathLinearSystemSolver.java:43-54: |R_jj| <= 1e-5 -> SingularMatrixSolverException
+    carrying getRank(0.01)."""
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((3, 6))
+    W = A.T @ A  # rank 3, 6x6
+    with pytest.raises(O.SingularMatrixError) as ei:
+        O.solve(W, np.ones(6))
+    assert ei.value.apparent_rank == 3
+
+
+def test_half_leaves_empty_rows_untouched_and_threads_agree():
+    rng = np.random.default_rng(2)
+    from conftest import random_problem
+    ptr, idx, val, Y0 = random_problem(300, 50, 8, 6, seed=3, empty_users=4)
+    G = O.transpose_times_self(Y0)
+    out1 = np.full((300, 6), 7.0, np.float32)
+    out8 = np.full((300, 6), 7.0, np.float32)
+    O.als_half(ptr, idx, val, Y0, G, out1, n_threads=1)
+    O.als_half(ptr, idx, val, Y0, G, out8, n_threads=8)
+    assert np.array_equal(out1, out8)
+    assert np.all(out1[:4] == 7.0) and not np.any(out1[4:] == 7.0)
+
+
+def test_half_matches_dense_normal_equations():
+    """Worker.call (:438-502) restated densely in numpy fp64."""
+    from conftest import random_problem
+    k = 5
+    ptr, idx, val, Y0 = random_problem(40, 30, 6, k, seed=4, neg_fraction=0.3)
+    G = O.transpose_times_self(Y0)
+    out = np.zeros((40, k), np.float32)
+    O.als_half(ptr, idx, val, Y0, G, out, alpha=2.0, lam=0.05)
+    Yd = Y0.astype(np.float64)
+    for u in range(40):
+        e = slice(ptr[u], ptr[u + 1])
+        y = Yd[idx[e]]
+        r = val[e].astype(np.float64)
+        W = G + (y.T * (2.0 * np.abs(r))) @ y + 0.05 * 2.0 * len(r) * np.eye(k)
+        b = (y.T * np.where(r > 0, 1 + 2.0 * np.abs(r), 0.0)).sum(axis=1)
+        assert np.abs(out[u] - np.linalg.solve(W, b)).max() < 1e-6
