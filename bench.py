@@ -259,7 +259,11 @@ def main():
     kernel = {"auto": 0, "simt": 1, "tcgen05": 2}[args.kernel]
 
     als = M.NativeALS(k, device=local_rank, kernel=kernel)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library launches on it and the CUDA events below are
+    # recorded on it, so the events bracket exactly the kernels that are timed
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     als.set_stream(stream.cuda_stream)
     if world > 1:
         import torch.distributed as dist

@@ -9,7 +9,10 @@
 // (CommonsMathLinearSystemSolver.java:41-45).  W_u is symmetric positive definite
 // whenever lambda*alpha*n_u > 0, so an LDL^T factorisation gives the same x_u; a
 // pivot <= the singularity threshold (or non-finite) reports ALS_E_SINGULAR instead
-// of emitting NaN/Inf (LinearSystemSolver.java:33-34 semantics).
+// of emitting NaN/Inf (LinearSystemSolver.java:33-34 semantics).  The rank-1 sums are
+// fp32 (exact products, <= ~1e-6 relative after summation); W_u itself, the
+// factorisation and the two triangular solves are fp64 like the reference's, so
+// ill-conditioned rows (few entries, large G) stay inside the 1e-4 parity bar.
 //
 // Data movement per row: n_u gathered factor rows of 4*KS bytes (coalesced float4,
 // staged in shared memory), n_u (index,value) pairs streamed, one 4*KS-byte row
@@ -41,6 +44,7 @@ struct RowUpdateParams {
 
 constexpr int kSimtThreads = 128;
 constexpr int kSimtChunk = 32;  // gathered rows staged per step
+constexpr int kFlushChunks = 8; // fp32 partial sums are folded into fp64 every 256 entries
 
 template <int KS>
 struct SimtShape {
@@ -49,8 +53,8 @@ struct SimtShape {
   static constexpr int TPT = (NTL + kSimtThreads - 1) / kSimtThreads;
   static constexpr int LDW = KS + 1;  // padded leading dimension of W in smem
   static constexpr size_t smem_bytes() {
-    return sizeof(float) * ((size_t)KS * LDW + (size_t)kSimtChunk * KS + 2 * kSimtChunk + 3 * KS) +
-           sizeof(int) * kSimtChunk + 16;
+    return sizeof(double) * ((size_t)KS * LDW + 2 * KS) +
+           sizeof(float) * ((size_t)kSimtChunk * KS + 2 * kSimtChunk) + sizeof(int) * kSimtChunk + 16;
   }
 };
 
@@ -59,14 +63,13 @@ __global__ void __launch_bounds__(kSimtThreads)
 row_update_simt_kernel(const RowUpdateParams p) {
   using S = SimtShape<KS>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* Ys = reinterpret_cast<float*>(smem_raw);  // [chunk][KS], 16B aligned
-  float* W = Ys + kSimtChunk * KS;                 // [KS][LDW]
-  float* wgt = W + KS * S::LDW;                    // [chunk] SYRK weight
-  float* cb = wgt + kSimtChunk;                    // [chunk] rhs weight
-  float* bvec = cb + kSimtChunk;                   // [KS]
-  float* invd = bvec + KS;                         // [KS]
-  float* xs = invd + KS;                           // [KS]
-  int* idx = reinterpret_cast<int*>(xs + KS);      // [chunk]
+  double* W = reinterpret_cast<double*>(smem_raw);  // [KS][LDW]
+  double* bvec = W + KS * S::LDW;                   // [KS]
+  double* invd = bvec + KS;                         // [KS]
+  float* Ys = reinterpret_cast<float*>(invd + KS);  // [chunk][KS], 16B aligned
+  float* wgt = Ys + kSimtChunk * KS;                // [chunk] SYRK weight
+  float* cb = wgt + kSimtChunk;                     // [chunk] rhs weight
+  int* idx = reinterpret_cast<int*>(cb + kSimtChunk);  // [chunk]
   __shared__ long long s_row;
   __shared__ int s_fail;
 
@@ -105,6 +108,42 @@ row_update_simt_kernel(const RowUpdateParams p) {
 #pragma unroll
       for (int e = 0; e < 8; e++) acc[t][e] = make_float2(0.f, 0.f);
     float bacc = 0.f;
+    double bsum = 0.0;
+
+    // W starts as G + lambda*alpha*n_u*I in fp64 (lower triangle; ALS.java:447-450, 488-492).
+    // The fp32 rank-1 partial sums are folded into it every kFlushChunks chunks, so a row
+    // with thousands of entries never carries more than a few hundred terms in fp32.
+    const bool add_g = !p.loss_ignores_unspecified;
+    for (int e = tid; e < KS * KS; e += kSimtThreads) {
+      const int r = e / KS, c = e % KS;
+      if (c <= r) {
+        double v = 0.0;  // padding rows/columns (k < KS) stay zero and are never factorised
+        if (r < k && add_g) v = p.G[r * KS + c];
+        if (r == c && r < k) v += p.lambda_alpha * (double)nu;
+        W[r * S::LDW + c] = v;
+      }
+    }
+    __syncthreads();
+    auto flush_tiles = [&]() {
+#pragma unroll
+      for (int t = 0; t < S::TPT; t++) {
+        if (ti[t] < 0) continue;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int r = 4 * ti[t] + i, c = 4 * tj[t] + j;
+            const float2 v2 = acc[t][2 * i + j / 2];
+            if (c <= r) W[r * S::LDW + c] += (double)((j & 1) ? v2.y : v2.x);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[t][e] = make_float2(0.f, 0.f);
+      }
+      bsum += (double)bacc;
+      bacc = 0.f;
+    };
+    int chunks_since_flush = 0;
 
     for (long long c0 = e0; c0 < e1; c0 += kSimtChunk) {
       const int n = (int)min((long long)kSimtChunk, e1 - c0);
@@ -149,47 +188,34 @@ row_update_simt_kernel(const RowUpdateParams p) {
         }
         if (tid < KS) bacc = fmaf(cb[e], Ys[e * KS + tid], bacc);
       }
-    }
-
-    // W = G + acc (+ lambda*alpha*n_u on the diagonal); lower triangle only.
-    const bool add_g = !p.loss_ignores_unspecified;
-#pragma unroll
-    for (int t = 0; t < S::TPT; t++) {
-      if (ti[t] < 0) continue;
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int r = 4 * ti[t] + i, c = 4 * tj[t] + j;
-          const float2 v2 = acc[t][2 * i + j / 2];
-          double v = (double)((j & 1) ? v2.y : v2.x);
-          if (add_g) v += p.G[r * KS + c];
-          if (r == c) v += p.lambda_alpha * (double)nu;
-          W[r * S::LDW + c] = (float)v;
-        }
+      if (++chunks_since_flush == kFlushChunks) {
+        flush_tiles();  // each tile entry is owned by exactly one thread: no barrier needed
+        chunks_since_flush = 0;
       }
     }
-    if (tid < KS) bvec[tid] = bacc;
+
+    flush_tiles();  // last partial sums
+    if (tid < KS) bvec[tid] = bsum;
 
     // LDL^T, right-looking, one barrier per column. Column j keeps the unscaled
     // values W[i][j] = L[i][j]*d_j; invd[j] = 1/d_j.
     const int tx = tid % 16, ty = tid / 16;
     for (int j = 0; j < k; j++) {
       __syncthreads();
-      const float d = W[j * S::LDW + j];
-      if (!(d > p.threshold) || !isfinite(d)) {
+      const double d = W[j * S::LDW + j];
+      if (!(d > (double)p.threshold) || !isfinite(d)) {
         if (tid == 0) {
-          report_error(p.status, ALS_E_SINGULAR, p.which, p.row_offset + row, d);
+          report_error(p.status, ALS_E_SINGULAR, p.which, p.row_offset + row, (float)d);
           s_fail = 1;
         }
         break;
       }
-      const float id = 1.0f / d;
+      const double id = 1.0 / d;
       if (tid == 0) invd[j] = id;
       for (int i = j + 1 + ty; i < k; i += kSimtThreads / 16) {
-        const float lij = W[i * S::LDW + j] * id;
+        const double lij = W[i * S::LDW + j] * id;
         for (int c = j + 1 + tx; c <= i; c += 16) {
-          W[i * S::LDW + c] = fmaf(-lij, W[c * S::LDW + j], W[i * S::LDW + c]);
+          W[i * S::LDW + c] = fma(-lij, W[c * S::LDW + j], W[i * S::LDW + c]);
         }
       }
     }
@@ -200,8 +226,8 @@ row_update_simt_kernel(const RowUpdateParams p) {
     if (tid < kWarp) {
       // forward: z = L^{-1} b   (column oriented)
       for (int j = 0; j < k; j++) {
-        const float t = bvec[j] * invd[j];
-        for (int i = j + 1 + tid; i < k; i += kWarp) bvec[i] = fmaf(-W[i * S::LDW + j], t, bvec[i]);
+        const double t = bvec[j] * invd[j];
+        for (int i = j + 1 + tid; i < k; i += kWarp) bvec[i] = fma(-W[i * S::LDW + j], t, bvec[i]);
         __syncwarp();
       }
       // y = D^{-1} z
@@ -209,15 +235,15 @@ row_update_simt_kernel(const RowUpdateParams p) {
       __syncwarp();
       // backward: x = L^{-T} y   (row j of W holds L[j][i]*d_i)
       for (int j = k - 1; j >= 0; j--) {
-        const float xj = bvec[j];
+        const double xj = bvec[j];
         for (int i = tid; i < j; i += kWarp)
-          bvec[i] = fmaf(-W[j * S::LDW + i] * invd[i], xj, bvec[i]);
+          bvec[i] = fma(-W[j * S::LDW + i] * invd[i], xj, bvec[i]);
         __syncwarp();
       }
       bool bad = false;
       float* dst = p.out + (p.row_offset + row) * KS;
       for (int i = tid; i < k; i += kWarp) {
-        const float x = bvec[i];
+        const float x = (float)bvec[i];  // CommonsMathSolver.solveDToF's (float) cast
         bad |= !isfinite(x);
         dst[i] = x;
       }

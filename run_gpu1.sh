@@ -1,0 +1,13 @@
+#!/bin/bash
+# GPU session 1: correctness first, then first numbers.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+free -g >> gpurun_out/gpu.txt; nproc >> gpurun_out/gpu.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -30 gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+tail -5 gpurun_out/smoke.log
+timeout 600 python bench.py --config c2 --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench c2 rc=$?"
+tail -c 3000 gpurun_out/bench_c2.json; tail -5 gpurun_out/bench_c2.err
+timeout 1200 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "bench c3 rc=$?"
+tail -c 3000 gpurun_out/bench_c3.json; tail -5 gpurun_out/bench_c3.err
