@@ -19,6 +19,7 @@
 // written.  Arithmetic: lower-triangular 4x4 register tiles, packed fp32x2 FMAs.
 #pragma once
 #include "common.cuh"
+#include "solve_fp64.cuh"
 
 namespace als {
 
@@ -71,7 +72,6 @@ row_update_simt_kernel(const RowUpdateParams p) {
   float* cb = wgt + kSimtChunk;                     // [chunk] rhs weight
   int* idx = reinterpret_cast<int*>(cb + kSimtChunk);  // [chunk]
   __shared__ long long s_row;
-  __shared__ int s_fail;
 
   const int tid = threadIdx.x;
   const int k = p.k;
@@ -93,7 +93,6 @@ row_update_simt_kernel(const RowUpdateParams p) {
     __syncthreads();
     if (tid == 0) {
       s_row = (long long)atomicAdd(p.ticket, 1ULL);
-      s_fail = 0;
     }
     __syncthreads();
     const long long row = s_row;
@@ -197,58 +196,9 @@ row_update_simt_kernel(const RowUpdateParams p) {
     flush_tiles();  // last partial sums
     if (tid < KS) bvec[tid] = bsum;
 
-    // LDL^T, right-looking, one barrier per column. Column j keeps the unscaled
-    // values W[i][j] = L[i][j]*d_j; invd[j] = 1/d_j.
-    const int tx = tid % 16, ty = tid / 16;
-    for (int j = 0; j < k; j++) {
-      __syncthreads();
-      const double d = W[j * S::LDW + j];
-      if (!(d > (double)p.threshold) || !isfinite(d)) {
-        if (tid == 0) {
-          report_error(p.status, ALS_E_SINGULAR, p.which, p.row_offset + row, (float)d);
-          s_fail = 1;
-        }
-        break;
-      }
-      const double id = 1.0 / d;
-      if (tid == 0) invd[j] = id;
-      for (int i = j + 1 + ty; i < k; i += kSimtThreads / 16) {
-        const double lij = W[i * S::LDW + j] * id;
-        for (int c = j + 1 + tx; c <= i; c += 16) {
-          W[i * S::LDW + c] = fma(-lij, W[c * S::LDW + j], W[i * S::LDW + c]);
-        }
-      }
-    }
-    __syncthreads();
-    if (s_fail) continue;
-
-    // Solve L D L^T x = b with warp 0 (k sequential steps each way).
-    if (tid < kWarp) {
-      // forward: z = L^{-1} b   (column oriented)
-      for (int j = 0; j < k; j++) {
-        const double t = bvec[j] * invd[j];
-        for (int i = j + 1 + tid; i < k; i += kWarp) bvec[i] = fma(-W[i * S::LDW + j], t, bvec[i]);
-        __syncwarp();
-      }
-      // y = D^{-1} z
-      for (int i = tid; i < k; i += kWarp) bvec[i] *= invd[i];
-      __syncwarp();
-      // backward: x = L^{-T} y   (row j of W holds L[j][i]*d_i)
-      for (int j = k - 1; j >= 0; j--) {
-        const double xj = bvec[j];
-        for (int i = tid; i < j; i += kWarp)
-          bvec[i] = fma(-W[j * S::LDW + i] * invd[i], xj, bvec[i]);
-        __syncwarp();
-      }
-      bool bad = false;
-      float* dst = p.out + (p.row_offset + row) * KS;
-      for (int i = tid; i < k; i += kWarp) {
-        const float x = (float)bvec[i];  // CommonsMathSolver.solveDToF's (float) cast
-        bad |= !isfinite(x);
-        dst[i] = x;
-      }
-      if (bad) report_error(p.status, ALS_E_NONFINITE, p.which, p.row_offset + row, 0.f);
-    }
+    // fp64 LDL^T + solves (first barrier inside covers the W / bvec writes above)
+    ldlt_solve_fp64<KS>(W, bvec, invd, k, tid, 0, (double)p.threshold, p.status, p.which,
+                        p.row_offset + row, p.out + (p.row_offset + row) * KS);
   }
 }
 
