@@ -31,11 +31,15 @@ CONFIGS = {
     "c1": dict(users=10_000, items=2_000, nnz_per_user=20, k=16),
     "c2": dict(users=1_000_000, items=100_000, nnz_per_user=50, k=32),
     "c3": dict(users=10_000_000, items=1_000_000, nnz_per_user=100, k=64),
+    # c3 at 1/5 scale (same entries per user and per item): profiling-only, ncu replays need
+    # the working set small enough to save/restore between passes
+    "c3p": dict(users=2_000_000, items=200_000, nnz_per_user=100, k=64),
 }
 WORKLOAD_NAMES = {
     "c1": "10k x 2k, 20 nnz/user, k=16",
     "c2": "1M x 100k, 50 nnz/user, k=32",
     "c3": "10M x 1M, 100 nnz/user, k=64 (headline)",
+    "c3p": "2M x 200k, 100 nnz/user, k=64 (1/5-scale headline, profiling only)",
 }
 
 
@@ -338,6 +342,7 @@ def main():
                        "algorithmic_bytes_per_launch": by if dom == "x" else bx},
         "gramian_ms_per_iteration": tm.gramian_ms / args.steps,
         "exchange_ms_per_iteration": tm.exchange_ms / args.steps,
+        "fp64_retry_rows_per_iteration": tm.fp64_retry_rows / args.steps,
         "iteration_frac_of_hbm_roof": algorithmic_bytes(U, I, nnz, k) / world /
                                       (ms_per_step * 1e-3) / 1e9 / peak,
     }

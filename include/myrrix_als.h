@@ -181,6 +181,7 @@ typedef struct als_timings {
   double update_y_ms;       /* row-update kernel over items, summed */
   double exchange_ms;       /* multi-GPU factor exchange, summed */
   int32_t n_half_x, n_half_y;
+  int64_t fp64_retry_rows;  /* rows the fp32 tensor-core path handed to the fp64 kernel */
 } als_timings;
 int als_profile_enable(als_handle *h, int32_t on);
 int als_get_timings(als_handle *h, als_timings *out, int32_t reset);

@@ -82,6 +82,10 @@ struct als_handle {
   int g_partials = 0;
   DeviceStatus* d_status = nullptr;
   unsigned long long* d_ticket = nullptr;
+  int* d_retry_rows = nullptr;   // rows the tensor-core kernel handed to the fp64 kernel
+  long long retry_cap = 0;
+  int* d_retry_count = nullptr;
+  long long* d_retry_total = nullptr;
   double* d_scratch = nullptr;  // rank kernel scratch + probe output
   int* d_rank = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -300,13 +304,42 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
   p.which = which;
   p.status = h->d_status;
   p.ticket = h->d_ticket;
+  p.row_list = nullptr;
+  p.row_list_count = nullptr;
+  p.retry_rows = nullptr;
+  p.retry_count = nullptr;
   CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned long long), h->stream));
-  cudaEvent_t a;
-  prof_begin(h, &a);
   int rc = ALS_OK;
   if (h->kernel == ALS_KERNEL_TCGEN05) {
+    if (h->retry_cap < R.rows) {
+      dev_free(h, &h->d_retry_rows, (size_t)h->retry_cap);
+      h->retry_cap = R.rows;
+      if ((rc = dev_alloc(h, &h->d_retry_rows, (size_t)h->retry_cap)) != ALS_OK) return rc;
+    }
+    CU(h, cudaMemsetAsync(h->d_retry_count, 0, sizeof(int), h->stream));
+  }
+  cudaEvent_t a;
+  prof_begin(h, &a);
+  if (h->kernel == ALS_KERNEL_TCGEN05) {
+    p.retry_rows = h->d_retry_rows;
+    p.retry_count = h->d_retry_count;
     rc = launch_row_update_umma(h->ks, p, h->sm_count, h->stream, h->err, sizeof(h->err));
-    if (rc == ALS_OK) h->launches += 1;
+    if (rc == ALS_OK) {
+      h->launches += 1;
+      // fp64 re-solve of the rows the fp32 tensor-core path refused (normally none): the
+      // CUDA-core kernel in row-list mode; it exits immediately when the list is empty.
+      accumulate_count_kernel<<<1, 1, 0, h->stream>>>(h->d_retry_count, h->d_retry_total);
+      RowUpdateParams q = p;
+      q.row_list = h->d_retry_rows;
+      q.row_list_count = h->d_retry_count;
+      q.retry_rows = nullptr;
+      q.retry_count = nullptr;
+      switch (h->ks) {
+        case 32: rc = launch_simt_t<32>(h, q); break;
+        case 64: rc = launch_simt_t<64>(h, q); break;
+        default: rc = ALS_E_UNSUPPORTED; break;
+      }
+    }
   } else {
     switch (h->ks) {
       case 4: rc = launch_simt_t<4>(h, p); break;
@@ -494,6 +527,9 @@ int als_create(const als_config* cfg, als_handle** out) {
   if ((rc = dev_alloc(h, &h->d_status, 1)) != ALS_OK) return rc;
   if ((rc = dev_alloc(h, &h->d_ticket, 1)) != ALS_OK) return rc;
   if ((rc = dev_alloc(h, &h->d_rank, 1)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &h->d_retry_count, 1)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &h->d_retry_total, 1)) != ALS_OK) return rc;
+  CU(h, cudaMemsetAsync(h->d_retry_total, 0, sizeof(long long), h->stream));
   const size_t scratch = (size_t)2 * h->k * h->k + 2 * h->k + 1;
   if ((rc = dev_alloc(h, &h->d_scratch, scratch > 10000 ? scratch : 10000)) != ALS_OK) return rc;
   CU(h, cudaMemsetAsync(h->d_status, 0, sizeof(DeviceStatus), h->stream));
@@ -512,6 +548,7 @@ int als_destroy(als_handle* h) {
   free_csr(h, &h->by_item);
   cudaFree(h->X); cudaFree(h->Y); cudaFree(h->G); cudaFree(h->G_partial);
   cudaFree(h->d_status); cudaFree(h->d_ticket); cudaFree(h->d_rank); cudaFree(h->d_scratch);
+  cudaFree(h->d_retry_rows); cudaFree(h->d_retry_count); cudaFree(h->d_retry_total);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return ALS_OK;
@@ -746,11 +783,15 @@ int als_get_timings(als_handle* h, als_timings* out, int32_t reset) {
   cudaStreamSynchronize(h->stream);
   prof_drain(h);
   h->tm.launches = h->launches;
+  long long retried = 0;
+  cudaMemcpy(&retried, h->d_retry_total, sizeof(long long), cudaMemcpyDeviceToHost);
+  h->tm.fp64_retry_rows = retried;
   *out = h->tm;
   if (reset) {
     memset(&h->tm, 0, sizeof(h->tm));
     h->tm.struct_size = (int32_t)sizeof(als_timings);
     h->launches = 0;
+    cudaMemsetAsync(h->d_retry_total, 0, sizeof(long long), h->stream);
   }
   return ALS_OK;
 }

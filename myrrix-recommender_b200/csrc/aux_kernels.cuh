@@ -46,6 +46,10 @@ __global__ void build_ptr_unpack_kernel(const int* __restrict__ keys_sorted,
   }
 }
 
+__global__ void accumulate_count_kernel(const int* count, long long* total) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *total += (long long)*count;
+}
+
 __global__ void fill_ptr_zero_kernel(long long* ptr, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) ptr[i] = 0;

@@ -41,6 +41,12 @@ struct RowUpdateParams {
   int which;  // 0 = X half, 1 = Y half (for error reports)
   DeviceStatus* status;
   unsigned long long* ticket;  // zeroed before launch
+  // Row-list mode (CUDA-core kernel): process only row_list[0 .. *row_list_count).
+  const int* row_list;
+  const int* row_list_count;
+  // Filled by the tensor-core kernel: rows it refused (singular / ill-conditioned in fp32).
+  int* retry_rows;
+  int* retry_count;
 };
 
 constexpr int kSimtThreads = 128;
@@ -95,8 +101,13 @@ row_update_simt_kernel(const RowUpdateParams p) {
       s_row = (long long)atomicAdd(p.ticket, 1ULL);
     }
     __syncthreads();
-    const long long row = s_row;
-    if (row >= p.n_rows) break;
+    long long row = s_row;
+    if (p.row_list) {
+      if (row >= (long long)*p.row_list_count) break;
+      row = p.row_list[row];
+    } else if (row >= p.n_rows) {
+      break;
+    }
     const long long e0 = p.row_ptr[row], e1 = p.row_ptr[row + 1];
     const long long nu = e1 - e0;
     if (nu == 0) continue;  // not in the reference's map: leave the factor row untouched

@@ -55,6 +55,16 @@ __device__ __forceinline__ void bar_sync(int id, int n_threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
+// ---- register re-balancing between warp roles (whole warpgroups only) ---------------
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ---- TMEM --------------------------------------------------------------------
 // One full warp allocates `cols` (power of two >= 32) columns; base address lands in smem.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
