@@ -35,6 +35,14 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
                : "r"(a));
   return v;
 }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32x2(uint32_t a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
@@ -48,41 +56,44 @@ template <int KS>
 struct CholWarp {
   static_assert(KS == 32 || KS == 64, "in-register Cholesky supports k = 32 or 64");
   static constexpr bool kTwoRows = (KS == 64);
-  static constexpr int kPlane = KS * (KS + 1) / 2;  // packed lower triangle, column-major
+  // W planes are "pair-packed lower triangles": for column pair P = (2P, 2P+1) the rows
+  // i >= 2P are stored as float2 at float offset offP(P) + 2*(i - 2P).  (The .y slot of row
+  // i = 2P is above the diagonal and holds 0.)  Consecutive lanes (rows) touch consecutive
+  // 8-byte words: conflict-free for both the drain's stores and the Cholesky warp's loads.
+  static constexpr int kPlane = KS * KS / 2 + KS;
   static constexpr int kColBuf = KS + 8;            // column + z_j + d_j, 16-byte multiple
   static constexpr int kBlocks = KS / 8;
   static constexpr int kP1 = kTwoRows ? 32 : 4;     // pairs in row lane+32 (dummy 4 for KS=32)
-
-  // offset of column j inside a packed lower-triangular plane: element (i,j), i >= j, is at
-  // off(j) + i - j
-  __host__ __device__ static constexpr int off(int j) { return j * KS - j * (j - 1) / 2; }
+  __host__ __device__ static constexpr int offP(int P) { return 2 * (KS * P - P * (P - 1)); }
 
   struct Rows {
     float2 A0[16];   // row `lane`,    columns 0..31
     float2 A1[kP1];  // row `lane+32`, columns 0..63 (KS = 64 only)
   };
 
-  // planes p0 + p1 (shared addresses): packed lower triangles whose sum is W_u (G and
+  // planes p0 + p1 (shared addresses): pair-packed lower triangles whose sum is W_u (G and
   // lambda*alpha*n_u already folded in by the drain warps).
   __device__ static __forceinline__ void load(uint32_t p0, uint32_t p1, int lane, Rows& R) {
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-      float v = 0.f;
-      if (j <= lane) {
-        const uint32_t o = (uint32_t)(off(j) - j + lane) * 4u;
-        v = lds_f32(p0 + o) + lds_f32(p1 + o);
+    for (int P = 0; P < 16; P++) {
+      float2 v = make_float2(0.f, 0.f);
+      if (lane >= 2 * P) {
+        const uint32_t o = (uint32_t)(offP(P) + 2 * (lane - 2 * P)) * 4u;
+        const float2 a = lds_f32x2(p0 + o), c = lds_f32x2(p1 + o);
+        v = make_float2(a.x + c.x, a.y + c.y);
       }
-      if (j & 1) R.A0[j >> 1].y = v; else R.A0[j >> 1].x = v;
+      R.A0[P] = v;
     }
     if (kTwoRows) {
 #pragma unroll
-      for (int j = 0; j < 64; j++) {
-        float v = 0.f;
-        if (j <= lane + 32) {
-          const uint32_t o = (uint32_t)(off(j) - j + lane + 32) * 4u;
-          v = lds_f32(p0 + o) + lds_f32(p1 + o);
+      for (int P = 0; P < 32; P++) {
+        float2 v = make_float2(0.f, 0.f);
+        if (lane + 32 >= 2 * P) {
+          const uint32_t o = (uint32_t)(offP(P) + 2 * (lane + 32 - 2 * P)) * 4u;
+          const float2 a = lds_f32x2(p0 + o), c = lds_f32x2(p1 + o);
+          v = make_float2(a.x + c.x, a.y + c.y);
         }
-        if (j & 1) R.A1[j >> 1].y = v; else R.A1[j >> 1].x = v;
+        R.A1[P] = v;
       }
     }
   }
