@@ -882,6 +882,17 @@ int als_get_interaction_rows(als_handle* h, int32_t by_column, int64_t first_row
   return ALS_OK;
 }
 
+#ifdef ALS_PROFILE_WAITS
+// debug build only (scripts/wait_profile.py): read and clear the wait-cycle counters
+int als_debug_wait_cycles(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, als::umma::g_wait_cycles, sizeof(unsigned long long) * 16);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(als::umma::g_wait_cycles, z, sizeof(z));
+  return 0;
+}
+#endif
+
 // ---- multi-GPU ---------------------------------------------------------------
 int als_comm_unique_id_size(void) { return (int)sizeof(ncclUniqueId); }
 

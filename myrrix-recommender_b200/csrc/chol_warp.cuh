@@ -2,16 +2,19 @@
 // registers (fp32), k = KS in {32, 64}.
 //
 // Row distribution: lane l owns row l (and row l+32 when KS = 64); a row lives in
-// registers as float2 pairs along the column index.  Right-looking LDL^T in blocks of 8
-// columns: the block loop is a REAL loop (compact code -- the instruction footprint of a
-// fully unrolled 64-step sweep thrashes the instruction cache), made possible by rotating
-// each row's register array by 4 pairs after every block so the active block always sits
-// at register positions 0..3.  Per step j the (unscaled) column j, with zeros for rows <= j,
-// is published to a 2-deep shared-memory buffer; every lane reads it back as broadcast
-// 16-byte loads and applies   W[i][c] -= (w_i / d_j) * w_c   with packed fp32x2 FMAs, whole
-// 8-column groups at a time (finished groups are skipped by a warp-uniform test).
-// The forward substitution z = L^{-1} b is fused into the same sweep; D^{-1} is lane-local;
-// the backward substitution x = L^{-T} y runs block-wise with warp all-reduces.
+// registers as float2 pairs along the column index.  Panel-blocked right-looking LDL^T,
+// 8 columns per block, block loop is a REAL loop (compact code: the four roles of the
+// row-update kernel must share the instruction cache) made possible by rotating each row's
+// register array by 4 pairs per block so the active panel always sits at positions 0..3:
+//   1. eight cheap in-panel steps: the 8 owner lanes of rows jb..jb+7 publish their entry of
+//      column j (10 floats incl. pivot and z_j), every lane scales its own entry and updates
+//      only the panel columns of its rows; the forward substitution z = L^{-1} b rides along;
+//   2. every lane publishes the unscaled panel entries u_c[t] of its rows (transposed:
+//      Ut[t][c]), then one rank-8 update   W[i][c] -= sum_t L[i][jb+t] * u_c[t]   of all
+//      columns right of the panel: 16-byte broadcast loads + packed fp32x2 FMAs, whole
+//      8-column groups at a time (finished groups skipped by a warp-uniform test).
+// D^{-1} is lane-local; the backward substitution x = L^{-T} y runs block-wise with warp
+// all-reduces for the part below the block and an 8x8 unit-triangular solve inside it.
 //
 // This is the fast path of MatrixUtils.getSolver(Wu).solveDToF(b) (ALS.java:494): rows whose
 // pivots indicate a singular or ill-conditioned W_u (max diag / min pivot > cond_limit, or
@@ -22,30 +25,6 @@
 
 namespace als {
 
-// shared-space accessors (32-bit shared addresses: guarantees LDS/STS, no generic loads)
-__device__ __forceinline__ float lds_f32(uint32_t a) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(a));
-  return v;
-}
-__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts_f32x2(uint32_t a, float2 v) {
-  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
-}
-__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
-}
 __device__ __forceinline__ float fast_rcp(float d) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
@@ -61,9 +40,11 @@ struct CholWarp {
   // i = 2P is above the diagonal and holds 0.)  Consecutive lanes (rows) touch consecutive
   // 8-byte words: conflict-free for both the drain's stores and the Cholesky warp's loads.
   static constexpr int kPlane = KS * KS / 2 + KS;
-  static constexpr int kColBuf = KS + 8;            // column + z_j + d_j, 16-byte multiple
   static constexpr int kBlocks = KS / 8;
-  static constexpr int kP1 = kTwoRows ? 32 : 4;     // pairs in row lane+32 (dummy 4 for KS=32)
+  static constexpr int kP1 = kTwoRows ? 32 : 4;  // pairs in row lane+32 (dummy 4 for KS=32)
+  // per-warp scratch: 2 step buffers of 12 floats (8 column entries, z_j, d_j) + Ut[8][KS] + Lt[8][KS]
+  static constexpr int kStepBuf = 12;
+  static constexpr int kScratch = 2 * kStepBuf + 16 * KS;  // floats, 16-byte multiple
   __host__ __device__ static constexpr int offP(int P) { return 2 * (KS * P - P * (P - 1)); }
 
   struct Rows {
@@ -71,15 +52,16 @@ struct CholWarp {
     float2 A1[kP1];  // row `lane+32`, columns 0..63 (KS = 64 only)
   };
 
-  // planes p0 + p1 (shared addresses): pair-packed lower triangles whose sum is W_u (G and
+  // planes p0 + p1 (shared memory): pair-packed lower triangles whose sum is W_u (G and
   // lambda*alpha*n_u already folded in by the drain warps).
-  __device__ static __forceinline__ void load(uint32_t p0, uint32_t p1, int lane, Rows& R) {
+  __device__ static __forceinline__ void load(const float* p0, const float* p1, int lane, Rows& R) {
 #pragma unroll
     for (int P = 0; P < 16; P++) {
       float2 v = make_float2(0.f, 0.f);
       if (lane >= 2 * P) {
-        const uint32_t o = (uint32_t)(offP(P) + 2 * (lane - 2 * P)) * 4u;
-        const float2 a = lds_f32x2(p0 + o), c = lds_f32x2(p1 + o);
+        const int o = offP(P) + 2 * (lane - 2 * P);
+        const float2 a = *reinterpret_cast<const float2*>(p0 + o);
+        const float2 c = *reinterpret_cast<const float2*>(p1 + o);
         v = make_float2(a.x + c.x, a.y + c.y);
       }
       R.A0[P] = v;
@@ -89,8 +71,9 @@ struct CholWarp {
       for (int P = 0; P < 32; P++) {
         float2 v = make_float2(0.f, 0.f);
         if (lane + 32 >= 2 * P) {
-          const uint32_t o = (uint32_t)(offP(P) + 2 * (lane + 32 - 2 * P)) * 4u;
-          const float2 a = lds_f32x2(p0 + o), c = lds_f32x2(p1 + o);
+          const int o = offP(P) + 2 * (lane + 32 - 2 * P);
+          const float2 a = *reinterpret_cast<const float2*>(p0 + o);
+          const float2 c = *reinterpret_cast<const float2*>(p1 + o);
           v = make_float2(a.x + c.x, a.y + c.y);
         }
         R.A1[P] = v;
@@ -113,16 +96,18 @@ struct CholWarp {
     A[0] = t0; A[1] = t1; A[2] = t2; A[3] = t3;
   }
 
-  // colbuf: shared address of [2][kColBuf] floats private to this warp. b0/b1: rhs entries of
+  // scratch: kScratch floats of shared memory private to this warp. b0/b1: rhs entries of
   // this lane's rows. k: true feature count; padding rows (j >= k) must carry a unit diagonal
   // and are not judged. Returns (warp-uniform) true if the system was solved; x0/x1 then hold
   // the solution entries of rows lane / lane+32.
-  __device__ static __forceinline__ bool factor_solve(Rows& R, uint32_t colbuf, float b0, float b1,
+  __device__ static __forceinline__ bool factor_solve(Rows& R, float* scratch, float b0, float b1,
                                                       float threshold, float cond_limit, int lane,
                                                       int k, float& x0, float& x1) {
     constexpr unsigned FULL = 0xffffffffu;
     float2 (&A0)[16] = R.A0;
     float2 (&A1)[kP1] = R.A1;
+    float* Ut = scratch + 2 * kStepBuf;  // [8][KS] unscaled panel entries, transposed
+    float* Lt = Ut + 8 * KS;             // [8][KS] L panel entries, transposed
 
     // largest diagonal entry (for the conditioning check)
     float dmax;
@@ -140,75 +125,128 @@ struct CholWarp {
       for (int o = 16; o > 0; o >>= 1) mine = fmaxf(mine, __shfl_xor_sync(FULL, mine, o));
       dmax = mine;
     }
-    float dmin = dmax;
-    bool bad = !(dmax > threshold) || !isfinite(dmax);
     float inv0 = 0.f, inv1 = 0.f;  // 1/d of my rows
+    float d0 = dmax, d1 = dmax;    // pivots of my rows (judged after the sweep)
 
-    // ---- LDL^T + fused forward substitution, 8 columns per trip ---------------------------
-#pragma unroll 1
+#pragma unroll
     for (int b = 0; b < kBlocks; b++) {
       const int jb = 8 * b;
       const bool a0_live = jb < 32;     // row `lane` still has unfinished columns
-      const int groups = kBlocks - b;   // live 8-column groups of the longest row
+      const bool own_in0 = jb < 32;     // the panel's diagonal rows jb..jb+7 live in A0 (else A1)
+      const int tl = lane - (jb & 31);  // 0..7 on the lanes owning rows jb..jb+7
+      const bool owner = tl >= 0 && tl < 8;
+      // ---- 1. eight in-panel steps, two per trip; the panel's 4 pairs rotate by one pair per
+      //         trip so the active pair is always position 0 (compact code) ------------------
+#pragma unroll 1
+      for (int r = 0; r < 4; r++) {
 #pragma unroll
-      for (int t = 0; t < 8; t++) {
-        const int j = jb + t;
-        const uint32_t cb = colbuf + (uint32_t)((t & 1) * kColBuf) * 4u;
-        const float w0 = (t & 1) ? A0[t >> 1].y : A0[t >> 1].x;
-        const float w1 = kTwoRows ? ((t & 1) ? A1[t >> 1].y : A1[t >> 1].x) : 0.f;
-        // publish column j: rows <= j contribute zeros so finished columns are left alone
-        if (a0_live) sts_f32(cb + (uint32_t)lane * 4u, (lane > j) ? w0 : 0.f);
-        if (kTwoRows) sts_f32(cb + (uint32_t)(lane + 32) * 4u, (lane + 32 > j) ? w1 : 0.f);
-        if (lane == (j & 31)) {
-          const bool in0 = j < 32;
-          sts_f32(cb + (uint32_t)KS * 4u, in0 ? b0 : b1);        // z_j (unit-lower L)
-          sts_f32(cb + (uint32_t)(KS + 1) * 4u, in0 ? w0 : w1);  // pivot d_j
-        }
-        __syncwarp();
-        const float zj = lds_f32(cb + (uint32_t)KS * 4u);
-        const float d = lds_f32(cb + (uint32_t)(KS + 1) * 4u);
-        if (j < k) {
-          bad = bad || !(d > threshold) || !isfinite(d);
-          dmin = fminf(dmin, d);
-        }
-        const float inv = fast_rcp(d);
-        const float m0 = a0_live ? w0 * inv : 0.f;
-        const float m1 = w1 * inv;  // L[i][j]
-        if (lane == (j & 31)) { if (j < 32) inv0 = inv; else inv1 = inv; }
-        // keep L[i][j] in place of the unscaled entry
-        if (a0_live) { if (t & 1) A0[t >> 1].y = m0; else A0[t >> 1].x = m0; }
-        if (kTwoRows) { if (t & 1) A1[t >> 1].y = m1; else A1[t >> 1].x = m1; }
-        // forward substitution: b_i -= L[i][j] * z_j for rows below j
-        if (a0_live && lane > j) b0 = fmaf(-m0, zj, b0);
-        if (kTwoRows && lane + 32 > j) b1 = fmaf(-m1, zj, b1);
-        // trailing update, whole 8-column groups; group g covers columns jb+8g .. jb+8g+7
-        const float2 nm0 = make_float2(-m0, -m0), nm1 = make_float2(-m1, -m1);
-#pragma unroll
-        for (int g = 0; g < kBlocks; g++) {
-          if (g < groups) {  // warp-uniform
-            const float4 qa = lds_f32x4(cb + (uint32_t)(jb + 8 * g) * 4u);
-            const float4 qb = lds_f32x4(cb + (uint32_t)(jb + 8 * g + 4) * 4u);
-            const float2 c0 = make_float2(qa.x, qa.y), c1 = make_float2(qa.z, qa.w);
-            const float2 c2 = make_float2(qb.x, qb.y), c3 = make_float2(qb.z, qb.w);
-            if (kTwoRows) {
-              A1[4 * g + 0] = ffma2(nm1, c0, A1[4 * g + 0]);
-              A1[4 * g + 1] = ffma2(nm1, c1, A1[4 * g + 1]);
-              A1[4 * g + 2] = ffma2(nm1, c2, A1[4 * g + 2]);
-              A1[4 * g + 3] = ffma2(nm1, c3, A1[4 * g + 3]);
+        for (int h = 0; h < 2; h++) {
+          const int t = 2 * r + h;
+          const int j = jb + t;
+          float* sb = scratch + h * kStepBuf;
+          const float w0 = h ? A0[0].y : A0[0].x;
+          const float w1 = kTwoRows ? (h ? A1[0].y : A1[0].x) : 0.f;
+          if (owner) {
+            const float mine = own_in0 ? w0 : w1;
+            // slot of panel row tl in the rotated frame; rows <= j contribute zeros
+            sb[(tl - 2 * r) & 7] = (tl > t) ? mine : 0.f;
+            if (tl == t) {
+              sb[8] = own_in0 ? b0 : b1;  // z_j (unit-lower L)
+              sb[9] = mine;               // pivot d_j
             }
-            if (g < 4 && jb + 8 * g < 32) {  // row `lane` has only columns 0..31 (warp-uniform)
-              A0[4 * g + 0] = ffma2(nm0, c0, A0[4 * g + 0]);
-              A0[4 * g + 1] = ffma2(nm0, c1, A0[4 * g + 1]);
-              A0[4 * g + 2] = ffma2(nm0, c2, A0[4 * g + 2]);
-              A0[4 * g + 3] = ffma2(nm0, c3, A0[4 * g + 3]);
+          }
+          __syncwarp();
+          const float4 qa = *reinterpret_cast<const float4*>(sb);
+          const float4 qb = *reinterpret_cast<const float4*>(sb + 4);
+          const float2 zd = *reinterpret_cast<const float2*>(sb + 8);
+          const float zj = zd.x, d = zd.y;
+          const float inv = fast_rcp(d);
+          const float m0 = a0_live ? w0 * inv : 0.f;
+          const float m1 = w1 * inv;  // L[i][j]
+          if (tl == t) { if (own_in0) { inv0 = inv; d0 = d; } else { inv1 = inv; d1 = d; } }
+          // forward substitution: b_i -= L[i][j] * z_j for rows below j
+          if (a0_live && lane > j) b0 = fmaf(-m0, zj, b0);
+          if (kTwoRows && lane + 32 > j) b1 = fmaf(-m1, zj, b1);
+          // update the panel columns of my rows (zeros in sb leave finished columns alone)
+          const float2 c0 = make_float2(qa.x, qa.y), c1 = make_float2(qa.z, qa.w);
+          const float2 c2 = make_float2(qb.x, qb.y), c3 = make_float2(qb.z, qb.w);
+          if (a0_live) {
+            const float2 nm0 = make_float2(-m0, -m0);
+            A0[0] = ffma2(nm0, c0, A0[0]); A0[1] = ffma2(nm0, c1, A0[1]);
+            A0[2] = ffma2(nm0, c2, A0[2]); A0[3] = ffma2(nm0, c3, A0[3]);
+          }
+          if (kTwoRows) {
+            const float2 nm1 = make_float2(-m1, -m1);
+            A1[0] = ffma2(nm1, c0, A1[0]); A1[1] = ffma2(nm1, c1, A1[1]);
+            A1[2] = ffma2(nm1, c2, A1[2]); A1[3] = ffma2(nm1, c3, A1[3]);
+          }
+          // publish for the rank-8 update: the unscaled entry u_c[t] of my rows (rows inside or
+          // above the panel publish 0) and L[i][j]; keep L[i][j] in place of the entry
+          if (a0_live) {
+            Ut[t * KS + lane] = (lane >= jb + 8) ? w0 : 0.f;
+            Lt[t * KS + lane] = m0;
+            if (h) A0[0].y = m0; else A0[0].x = m0;
+          }
+          if (kTwoRows) {
+            Ut[t * KS + lane + 32] = (lane + 32 >= jb + 8) ? w1 : 0.f;
+            Lt[t * KS + lane + 32] = m1;
+            if (h) A1[0].y = m1; else A1[0].x = m1;
+          }
+        }
+        // rotate the panel pairs by one
+        if (a0_live) { const float2 t0 = A0[0]; A0[0] = A0[1]; A0[1] = A0[2]; A0[2] = A0[3]; A0[3] = t0; }
+        if (kTwoRows) { const float2 t1 = A1[0]; A1[0] = A1[1]; A1[1] = A1[2]; A1[2] = A1[3]; A1[3] = t1; }
+      }
+      __syncwarp();
+      // ---- 2. rank-8 update of the columns right of the panel ------------------------------
+      const int groups = kBlocks - b;  // live 8-column groups incl. the panel itself (g = 0)
+      if (groups > 1) {
+#pragma unroll 1
+        for (int t = 0; t < 8; t++) {
+          const float l0 = a0_live ? Lt[t * KS + lane] : 0.f;
+          const float l1 = kTwoRows ? Lt[t * KS + lane + 32] : 0.f;
+          const float2 nl0 = make_float2(-l0, -l0), nl1 = make_float2(-l1, -l1);
+          const float* ut = Ut + t * KS + jb;
+#pragma unroll
+          for (int g = 1; g < kBlocks; g++) {
+            if (g < groups) {  // warp-uniform
+              const float4 qa = *reinterpret_cast<const float4*>(ut + 8 * g);
+              const float4 qb = *reinterpret_cast<const float4*>(ut + 8 * g + 4);
+              const float2 c0 = make_float2(qa.x, qa.y), c1 = make_float2(qa.z, qa.w);
+              const float2 c2 = make_float2(qb.x, qb.y), c3 = make_float2(qb.z, qb.w);
+              if (kTwoRows) {
+                A1[4 * g + 0] = ffma2(nl1, c0, A1[4 * g + 0]);
+                A1[4 * g + 1] = ffma2(nl1, c1, A1[4 * g + 1]);
+                A1[4 * g + 2] = ffma2(nl1, c2, A1[4 * g + 2]);
+                A1[4 * g + 3] = ffma2(nl1, c3, A1[4 * g + 3]);
+              }
+              if (g < 4 && jb + 8 * g < 32) {  // row `lane` has only columns 0..31 (warp-uniform)
+                A0[4 * g + 0] = ffma2(nl0, c0, A0[4 * g + 0]);
+                A0[4 * g + 1] = ffma2(nl0, c1, A0[4 * g + 1]);
+                A0[4 * g + 2] = ffma2(nl0, c2, A0[4 * g + 2]);
+                A0[4 * g + 3] = ffma2(nl0, c3, A0[4 * g + 3]);
+              }
             }
           }
         }
       }
-      // rotate so the next block's columns sit at positions 0..3 (finished L goes to the end)
+      __syncwarp();  // Ut / Lt are rewritten by the next block
+      // rotate so the next panel sits at positions 0..3 (finished L goes to the end)
       if (kTwoRows) rotate_left4(A1);
       if (a0_live) rotate_left4(A0);
     }
+    // judge the pivots: smallest pivot vs threshold / largest diagonal entry
+    float dmin;
+    {
+      float mine = dmax;
+      if (lane < k) mine = fminf(mine, d0);
+      if (kTwoRows && lane + 32 < k) mine = fminf(mine, d1);
+      bool fin = isfinite(d0) && isfinite(d1) && isfinite(inv0) && isfinite(inv1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mine = fminf(mine, __shfl_xor_sync(FULL, mine, o));
+      dmin = __all_sync(FULL, fin) ? mine : -1.f;
+    }
+    const bool bad = !(dmax > threshold) || !isfinite(dmax) || !(dmin > threshold);
     // after KS/8 rotations of A1 (32 pairs, 8 blocks) and 4 of A0 (16 pairs) both arrays are
     // back in natural column order and hold L (unit lower, strictly below the diagonal).
     if (bad || !(dmin * cond_limit >= dmax)) return false;
@@ -216,7 +254,7 @@ struct CholWarp {
     // ---- y = D^{-1} z, then x = L^{-T} y, block-wise from the last block ---------------------
     x0 = b0 * inv0;
     x1 = kTwoRows ? b1 * inv1 : 0.f;
-#pragma unroll 1
+#pragma unroll
     for (int b = kBlocks - 1; b >= 0; b--) {
       const int jb = 8 * b;
       const bool in0 = jb < 32;  // the block's rows live in A0/x0 (else A1/x1)

@@ -68,10 +68,10 @@ struct Smem {
   static constexpr size_t off_g32 = off_planes + kWSlots * 2 * kPlaneBytes;
   static constexpr size_t off_bpart = off_g32 + kPlaneBytes;                    // [kBSlots][P][KS]
   static constexpr size_t off_colbuf = off_bpart + sizeof(float) * kBSlots * kProdWarps * KS;
-  static constexpr size_t off_bars = off_colbuf + sizeof(float) * kCholWarps * 2 * CW::kColBuf;
+  static constexpr size_t off_bars = off_colbuf + sizeof(float) * kCholWarps * CW::kScratch;
   static constexpr int kNumBars = 2 * kStages + 2 * kAccSlots + 2 * kCholWarps + 2 * kBSlots;
   static constexpr size_t off_misc = (off_bars + sizeof(uint64_t) * kNumBars + 15) / 16 * 16;
-  static constexpr size_t kTotal = off_misc + 64 + 1024;  // + slack for 1024-byte alignment
+  static constexpr size_t kTotal = off_misc + 64;
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -90,9 +90,10 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
   using G = StageGeom<KS>;
   using S = Smem<KS>;
   using CW = CholWarp<KS>;
-  extern __shared__ unsigned char smem_unaligned[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (SWIZZLE_128B atoms) comes from the declaration: no integer
+  // round-trip on the pointer, so the compiler keeps every access in the shared window
+  // (LDS/STS instead of generic loads); checked once below.
+  extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* ring = smem;
   float* g32 = reinterpret_cast<float*>(smem + S::off_g32);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_bars);
@@ -111,9 +112,12 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int k = p.k;
-  const uint32_t planes_s = smem_u32(smem + S::off_planes);
-  const uint32_t g32_s = smem_u32(g32);
-  const uint32_t bpart_s = smem_u32(smem + S::off_bpart);
+#ifdef ALS_PROFILE_WAITS
+  const long long prof_t0 = clock64();
+#endif
+  float* planes = reinterpret_cast<float*>(smem + S::off_planes);
+  float* bpart = reinterpret_cast<float*>(smem + S::off_bpart);
+  if (tid == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // operand atoms need 1024-byte alignment
 
   if (tid == 0) {
     for (int i = 0; i < kStages; i++) {
@@ -198,12 +202,9 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
           v.z += __shfl_xor_sync(kFull, v.z, off);
           v.w += __shfl_xor_sync(kFull, v.w, off);
         }
-        mbar_wait(&b_empty[bslot], (uint32_t)(((useq / kBSlots) & 1) ^ 1));
-        if (lane < CPR) {
-          const uint32_t a = bpart_s + (uint32_t)(((bslot * kProdWarps + pw) * KS + 4 * q) * 4);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y),
-                       "f"(v.z), "f"(v.w) : "memory");
-        }
+        mbar_wait_id(&b_empty[bslot], (uint32_t)(((useq / kBSlots) & 1) ^ 1), 0);
+        if (lane < CPR)
+          *reinterpret_cast<float4*>(bpart + (bslot * kProdWarps + pw) * KS + 4 * q) = v;
         __syncwarp();
         if (lane == 0) mbar_arrive(&b_full[bslot]);
         bacc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -256,8 +257,8 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
 
         const uint32_t sidx = cbase + (uint32_t)cst;
         const int slot = (int)(sidx % kStages);
-        mbar_wait(&empty[slot], ((sidx / kStages) & 1) ^ 1);
-        const uint32_t stage = smem_u32(ring) + (uint32_t)slot * G::kBytes;
+        mbar_wait_id(&empty[slot], ((sidx / kStages) & 1) ^ 1, 1);
+        unsigned char* stage = ring + (size_t)slot * G::kBytes;
 #pragma unroll
         for (int ps = 0; ps < NPASS; ps++) {
           const float ar = p.alpha * fabsf(r[ps]);
@@ -266,10 +267,10 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
           const float cb = p.reconstruct_r ? r[ps] : (r[ps] > 0.f ? 1.f + ar : 0.f);  // :480-482
           uint2 hi, lo;
           split_bf16x2(make_float4(y[ps].x * s, y[ps].y * s, y[ps].z * s, y[ps].w * s), hi, lo);
-          const uint32_t ah = stage + offs[ps];
-          const uint32_t al = (KS == 64) ? ah + 1024u : (ah ^ 64u);
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ah), "r"(hi.x), "r"(hi.y) : "memory");
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(al), "r"(lo.x), "r"(lo.y) : "memory");
+          const uint32_t oh = offs[ps];
+          const uint32_t ol = (KS == 64) ? oh + 1024u : (oh ^ 64u);
+          *reinterpret_cast<uint2*>(stage + oh) = hi;
+          *reinterpret_cast<uint2*>(stage + ol) = lo;
           bacc.x = fmaf(cb, y[ps].x, bacc.x);
           bacc.y = fmaf(cb, y[ps].y, bacc.y);
           bacc.z = fmaf(cb, y[ps].z, bacc.z);
@@ -304,14 +305,14 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
             const bool seg_first = (st % kSegStages) == 0;
             if (seg_first) {
               a = (int)(gseg % kAccSlots);
-              mbar_wait(&acc_empty[a], ((gseg / kAccSlots) & 1) ^ 1);
+              mbar_wait_id(&acc_empty[a], ((gseg / kAccSlots) & 1) ^ 1, 2);
               tc_fence_after_sync();
               d_tmem = tmem_base + (uint32_t)(a * G::kN);
             }
             const int slot = (int)(sidx % kStages);
-            mbar_wait(&full[slot], (sidx / kStages) & 1);
+            mbar_wait_id(&full[slot], (sidx / kStages) & 1, 3);
             tc_fence_after_sync();
-            const uint32_t sa = smem_u32(ring) + (uint32_t)slot * G::kBytes;
+            const uint32_t sa = smem_u32(ring + (size_t)slot * G::kBytes);
 #pragma unroll
             for (int ks = 0; ks < G::kKSteps; ks++) {
               const uint64_t desc = make_smem_desc(sa + ks * G::kKStepBytes, G::kLBO, G::kSBO);
@@ -352,15 +353,15 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
         const int nst = (cnt + E - 1) / E;
         const int nseg = (nst + kSegStages - 1) / kSegStages;
         const int ws = useq % kWSlots;
-        const uint32_t plane = planes_s + (uint32_t)((ws * 2 + (is_lo ? 1 : 0)) * kPlaneF) * 4u;
+        float* plane = planes + (ws * 2 + (is_lo ? 1 : 0)) * kPlaneF;
         const float lam_n = (float)(p.lambda_alpha * (double)cnt);
         if (useq >= kWSlots) {  // slot last held row useq - kWSlots: wait until it was loaded
           const int prev = useq - kWSlots;
-          mbar_wait(&w_empty[prev % kCholWarps], (uint32_t)((prev / kCholWarps) & 1));
+          mbar_wait_id(&w_empty[prev % kCholWarps], (uint32_t)((prev / kCholWarps) & 1), 4);
         }
         for (int seg = 0; seg < nseg; seg++, gseg++) {
           const int a = (int)(gseg % kAccSlots);
-          mbar_wait(&acc_full[a], (gseg / kAccSlots) & 1);
+          mbar_wait_id(&acc_full[a], (gseg / kAccSlots) & 1, 5);
           tc_fence_after_sync();
           const uint32_t taddr = tmem_base + lane_base + (uint32_t)(a * G::kN);
 #pragma unroll 1
@@ -379,20 +380,20 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
                   v.x = __uint_as_float(v0[jj]) + __uint_as_float(v1[jj]);
                   v.y = (i > j) ? __uint_as_float(v0[jj + 1]) + __uint_as_float(v1[jj + 1]) : 0.f;
                   const int P = j >> 1;
-                  const uint32_t o = (uint32_t)(2 * (KS * P - P * (P - 1)) + 2 * (i - j)) * 4u;
+                  const int o = 2 * (KS * P - P * (P - 1)) + 2 * (i - j);
                   if (seg == 0) {
                     // W = G + lambda*alpha*n_u*I + ... (ALS.java:447-450, 488-492): hi plane only
                     if (is_hi) {
-                      const float2 g = lds_f32x2(g32_s + o);
+                      const float2 g = *reinterpret_cast<const float2*>(g32 + o);
                       v.x += g.x + ((i == j && i < k) ? lam_n : 0.f);
                       v.y += g.y + ((i == j + 1 && i < k) ? lam_n : 0.f);
                     }
                   } else {
-                    const float2 old = lds_f32x2(plane + o);
+                    const float2 old = *reinterpret_cast<const float2*>(plane + o);
                     v.x += old.x;
                     v.y += old.y;
                   }
-                  sts_f32x2(plane + o, v);
+                  *reinterpret_cast<float2*>(plane + o) = v;
                 }
               }
             }
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
     // =========================== Cholesky warps ======================================
     reg_alloc<kRegsChol>();
     const int cw = warp - kFirstChol;
-    const uint32_t colbuf = smem_u32(smem + S::off_colbuf) + (uint32_t)(cw * 2 * CW::kColBuf) * 4u;
+    float* scratch = reinterpret_cast<float*>(smem + S::off_colbuf) + cw * CW::kScratch;
     int useq = 0;
     for (long long rb = blockIdx.x; rb < p.n_rows; rb += 32 * row_step) {
       int cnt_l = 0;
@@ -424,19 +425,18 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
         if (useq % kCholWarps != cw) { useq++; continue; }
         const long long row = rb + ib * row_step;
         const int ws = useq % kWSlots;
-        mbar_wait(&w_full[cw], (uint32_t)((useq / kCholWarps) & 1));
+        mbar_wait_id(&w_full[cw], (uint32_t)((useq / kCholWarps) & 1), 6);
         typename CW::Rows R;
-        CW::load(planes_s + (uint32_t)((ws * 2) * kPlaneF) * 4u,
-                 planes_s + (uint32_t)((ws * 2 + 1) * kPlaneF) * 4u, lane, R);
+        CW::load(planes + (ws * 2) * kPlaneF, planes + (ws * 2 + 1) * kPlaneF, lane, R);
         __syncwarp();
         if (lane == 0) mbar_arrive(&w_empty[cw]);  // slot free: the row now lives in registers
-        mbar_wait(&b_full[cw], (uint32_t)((useq / kBSlots) & 1));
+        mbar_wait_id(&b_full[cw], (uint32_t)((useq / kBSlots) & 1), 7);
         float b0 = 0.f, b1 = 0.f;
 #pragma unroll
         for (int w = 0; w < kProdWarps; w++) {
-          const uint32_t bp = bpart_s + (uint32_t)(((cw * kProdWarps + w) * KS + lane) * 4);
-          b0 += lds_f32(bp);
-          if (KS == 64) b1 += lds_f32(bp + 128u);
+          const float* bp = bpart + (cw * kProdWarps + w) * KS + lane;
+          b0 += bp[0];
+          if (KS == 64) b1 += bp[32];
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&b_empty[cw]);
@@ -452,8 +452,11 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
               if (j == lane + 32 && j >= k) { if (j & 1) R.A1[j >> 1].y = 1.f; else R.A1[j >> 1].x = 1.f; }
           }
         }
+        // All Cholesky warps enter the sweep together: they then run the same instruction
+        // stream in near lockstep, so the instruction cache sees one stream instead of eight.
+        bar_sync(1, kCholWarps * 32);
         float x0, x1;
-        const bool ok = CW::factor_solve(R, colbuf, b0, b1, p.threshold, kCondLimit, lane, k, x0, x1);
+        const bool ok = CW::factor_solve(R, scratch, b0, b1, p.threshold, kCondLimit, lane, k, x0, x1);
         if (ok) {
           float* dst = p.out + (p.row_offset + row) * KS;
           if (lane < k) dst[lane] = x0;
@@ -465,11 +468,16 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
         useq++;
       }
     }
+    // tail: warps without a row in the last round still meet the others at the barrier
+    if ((useq % kCholWarps) != 0 && cw >= (useq % kCholWarps)) bar_sync(1, kCholWarps * 32);
   }
 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
+#ifdef ALS_PROFILE_WAITS
+  if (tid == 0) atomicAdd(&g_wait_cycles[8], (unsigned long long)(clock64() - prof_t0));
+#endif
 }
 
 }  // namespace umma

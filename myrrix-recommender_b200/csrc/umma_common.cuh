@@ -44,6 +44,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Optional wait-time accounting (build with -DALS_PROFILE_WAITS): cycles each role spends
+// blocked on each kind of barrier, summed over all warps/CTAs into g_wait_cycles[id].
+#ifdef ALS_PROFILE_WAITS
+__device__ unsigned long long g_wait_cycles[16];
+__device__ __forceinline__ void mbar_wait_id(uint64_t* bar, uint32_t parity, int id) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  const long long dt = clock64() - t0;
+  if ((threadIdx.x & 31) == 0) atomicAdd(&g_wait_cycles[id], (unsigned long long)dt);
+}
+#else
+__device__ __forceinline__ void mbar_wait_id(uint64_t* bar, uint32_t parity, int) {
+  mbar_wait(bar, parity);
+}
+#endif
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
