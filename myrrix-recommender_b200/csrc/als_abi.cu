@@ -4,6 +4,7 @@
 // all HBM: both orientations of R (CSR by user, CSR by item), the two factor
 // matrices with a padded row stride, the fp64 Gramian and its partials.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
@@ -369,22 +370,22 @@ int exchange(als_handle* h, float* F, long long n_global) {
   return ALS_OK;
 }
 
-// Build the by-item orientation on the device: stable LSD radix sort of
-// (column key, row<<32|value) so each column keeps ascending row order.
-int build_transpose(als_handle* h) {
-  Csr& A = h->by_user;
-  Csr& T = h->by_item;
+// Build a transposed orientation on the device: stable LSD radix sort of
+// (column key, row<<32|value) so each column keeps ascending row order. Source A holds
+// rows [A.row_begin, A.row_begin + A.rows); only columns [col_begin, col_begin + n_cols)
+// may occur in it; T gets n_cols rows (row_begin = col_begin) whose indices are GLOBAL rows of A.
+int build_transpose_from(als_handle* h, const Csr& A, long long col_begin, long long n_cols, Csr* Tp) {
+  Csr& T = *Tp;
   free_csr(h, &T);
-  T.rows = h->n_items;
+  T.rows = n_cols;
   T.nnz = A.nnz;
-  T.row_begin = 0;
+  T.row_begin = col_begin;
   int rc;
   if ((rc = dev_alloc(h, &T.ptr, (size_t)T.rows + 1)) != ALS_OK) return rc;
   if ((rc = dev_alloc(h, &T.idx, (size_t)T.nnz)) != ALS_OK) return rc;
   if ((rc = dev_alloc(h, &T.val, (size_t)T.nnz)) != ALS_OK) return rc;
   if (A.nnz == 0) {
     CU(h, cudaMemsetAsync(T.ptr, 0, sizeof(long long) * ((size_t)T.rows + 1), h->stream));
-    h->have_by_item = true;
     return ALS_OK;
   }
   if (A.nnz >= (1LL << 31)) return fail(h, ALS_E_UNSUPPORTED, "nnz >= 2^31 per device");
@@ -403,10 +404,11 @@ int build_transpose(als_handle* h) {
     cleanup();
     return rc;
   }
-  expand_rows_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(A.ptr, A.rows, A.idx, A.val, keys_in,
+  expand_rows_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(A.ptr, A.rows, A.row_begin,
+                                                            (int)col_begin, A.idx, A.val, keys_in,
                                                             pk_in);
   int end_bit = 1;
-  while ((1LL << end_bit) < h->n_items && end_bit < 31) end_bit++;
+  while ((1LL << end_bit) < n_cols && end_bit < 31) end_bit++;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, pk_in,
                                                   pk_out, (int)n, 0, end_bit, h->stream);
   if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
@@ -426,8 +428,13 @@ int build_transpose(als_handle* h) {
   e = cudaStreamSynchronize(h->stream);
   cleanup();
   if (e != cudaSuccess) return fail(h, ALS_E_CUDA, "transpose: %s", cudaGetErrorString(e));
-  h->have_by_item = true;
   return ALS_OK;
+}
+
+int build_transpose(als_handle* h) {
+  int rc = build_transpose_from(h, h->by_user, 0, h->n_items, &h->by_item);
+  if (rc == ALS_OK) h->have_by_item = true;
+  return rc;
 }
 
 int upload_csr(als_handle* h, Csr* c, long long rows, long long row_begin, const long long* ptr,
@@ -802,25 +809,60 @@ int als_synth_interactions(als_handle* h, int64_t n_users, int64_t n_items, int3
   if (!h) return ALS_E_ARG;
   if (nnz_per_user <= 0 || nnz_per_user > n_items) return fail(h, ALS_E_ARG, "bad nnz_per_user");
   if (neg_fraction < 0.0 || neg_fraction > 1.0) return fail(h, ALS_E_ARG, "bad neg_fraction");
-  if (h->world != 1) return fail(h, ALS_E_UNSUPPORTED, "sharded synthesis not implemented yet");
   CU(h, cudaSetDevice(h->device));
   int rc = set_dims(h, n_users, n_items);
   if (rc != ALS_OK) return rc;
+  long long ub, ue, ib, ie;
+  local_block(h, h->n_users, &ub, &ue);
+  local_block(h, h->n_items, &ib, &ie);
   Csr& A = h->by_user;
   free_csr(h, &A);
   h->have_by_item = false;
-  A.rows = n_users;
-  A.nnz = (long long)n_users * nnz_per_user;
-  A.row_begin = 0;
+  A.rows = ue - ub;
+  A.nnz = A.rows * nnz_per_user;
+  A.row_begin = ub;
   if ((rc = dev_alloc(h, &A.ptr, (size_t)A.rows + 1)) != ALS_OK) return rc;
   if ((rc = dev_alloc(h, &A.idx, (size_t)A.nnz)) != ALS_OK) return rc;
   if ((rc = dev_alloc(h, &A.val, (size_t)A.nnz)) != ALS_OK) return rc;
   const unsigned int thr = (unsigned int)(neg_fraction * 16777216.0);
-  synth_rows_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(0, A.rows, n_items, nnz_per_user, seed,
+  synth_rows_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(ub, A.rows, n_items, nnz_per_user, seed,
                                                            thr, A.ptr, A.idx, A.val);
   h->launches += 1;
   CU(h, cudaGetLastError());
-  return build_transpose(h);
+  if (h->world == 1) return build_transpose(h);
+  // Sharded: the by-item orientation of this rank's item block. Every rank re-draws all
+  // users (counter-based generator, no communication), keeps its item block, transposes.
+  Csr tmp;
+  tmp.rows = n_users;
+  tmp.row_begin = 0;
+  long long* counts = nullptr;
+  if ((rc = dev_alloc(h, &counts, (size_t)n_users + 1)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &tmp.ptr, (size_t)n_users + 1)) != ALS_OK) return rc;
+  CU(h, cudaMemsetAsync(counts, 0, sizeof(long long) * ((size_t)n_users + 1), h->stream));
+  synth_item_block_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(
+      n_users, n_items, nnz_per_user, seed, thr, ib, ie, counts, nullptr, nullptr, nullptr);
+  {
+    void* stmp = nullptr;
+    size_t sbytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, sbytes, counts, tmp.ptr, (int)(n_users + 1), h->stream);
+    CU(h, cudaMalloc(&stmp, sbytes ? sbytes : 1));
+    cub::DeviceScan::ExclusiveSum(stmp, sbytes, counts, tmp.ptr, (int)(n_users + 1), h->stream);
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(stmp);
+  }
+  CU(h, cudaMemcpy(&tmp.nnz, tmp.ptr + n_users, sizeof(long long), cudaMemcpyDeviceToHost));
+  if ((rc = dev_alloc(h, &tmp.idx, (size_t)tmp.nnz)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &tmp.val, (size_t)tmp.nnz)) != ALS_OK) return rc;
+  synth_item_block_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(
+      n_users, n_items, nnz_per_user, seed, thr, ib, ie, nullptr, tmp.ptr, tmp.idx, tmp.val);
+  h->launches += 4;
+  CU(h, cudaGetLastError());
+  rc = build_transpose_from(h, tmp, ib, ie - ib, &h->by_item);
+  dev_free(h, &counts, (size_t)n_users + 1);
+  free_csr(h, &tmp);
+  if (rc != ALS_OK) return rc;
+  h->have_by_item = true;
+  return ALS_OK;
 }
 
 int als_synth_y0(als_handle* h, uint64_t seed) {

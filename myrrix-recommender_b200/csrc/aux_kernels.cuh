@@ -10,7 +10,10 @@ namespace als {
 
 // ---------------------------------------------------------------------------
 // CSR -> (key=column, value=row<<32|valbits) expansion for the stable radix sort.
+// row_offset: global index of local row 0 (stored in the packed value); col_offset is
+// subtracted from the column so the keys are local to the target shard.
 __global__ void expand_rows_kernel(const long long* __restrict__ row_ptr, long long n_rows,
+                                   long long row_offset, int col_offset,
                                    const int* __restrict__ col_idx, const float* __restrict__ val,
                                    int* __restrict__ keys, unsigned long long* __restrict__ packed) {
   // one warp per row: coalesced over the row's entries
@@ -20,8 +23,8 @@ __global__ void expand_rows_kernel(const long long* __restrict__ row_ptr, long l
   for (long long r = warp; r < n_rows; r += n_warps) {
     const long long e0 = row_ptr[r], e1 = row_ptr[r + 1];
     for (long long e = e0 + lane; e < e1; e += kWarp) {
-      keys[e] = col_idx[e];
-      packed[e] = ((unsigned long long)(unsigned int)r << 32) |
+      keys[e] = col_idx[e] - col_offset;
+      packed[e] = ((unsigned long long)(unsigned int)(r + row_offset) << 32) |
                   (unsigned long long)__float_as_uint(val[e]);
     }
   }
@@ -109,6 +112,42 @@ __global__ void synth_rows_kernel(long long row_begin, long long n_local_rows, l
     if (j == 0) row_ptr[r] = r * (long long)nnz_per_user;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) row_ptr[n_local_rows] = total;
+}
+
+// Sharded by-item orientation: every rank regenerates ALL users' draws (counter-based, no
+// communication) but keeps only the entries whose item falls in its own item block.
+// Pass 1 (counts != nullptr): counts[u] = kept entries of user u. Pass 2: write them at
+// row_ptr[u].. in ascending item order (the generator's j order).
+__global__ void synth_item_block_kernel(long long n_users, long long n_items, int nnz_per_user,
+                                        unsigned long long seed, unsigned int neg_threshold_24,
+                                        long long item_begin, long long item_end,
+                                        long long* __restrict__ counts,
+                                        const long long* __restrict__ row_ptr,
+                                        int* __restrict__ col_idx, float* __restrict__ val) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // strata that can intersect [item_begin, item_end)
+  const int j_lo = (int)((item_begin * nnz_per_user) / n_items);
+  int j_hi = (int)(((item_end - 1) * nnz_per_user) / n_items) + 2;  // +margin: filtered exactly below
+  if (j_hi > nnz_per_user) j_hi = nnz_per_user;
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < n_users; u += stride) {
+    long long n = 0;
+    const long long base = counts ? 0 : row_ptr[u];
+    for (int j = (j_lo > 0 ? j_lo - 1 : 0); j < j_hi; j++) {
+      const unsigned long long h = synth_hash(seed, (unsigned long long)u, (unsigned long long)j);
+      const long long lo = ((long long)j * n_items) / nnz_per_user;
+      const long long hi = ((long long)(j + 1) * n_items) / nnz_per_user;
+      const long long item = lo + (long long)((h >> 32) % (unsigned long long)(hi - lo));
+      if (item < item_begin || item >= item_end) continue;
+      if (!counts) {
+        float sgn = (float)(1 + (int)((h & 0xffffULL) % 5ULL));
+        if (((h >> 8) & 0xffffffULL) < neg_threshold_24) sgn = -sgn;
+        col_idx[base + n] = (int)item;
+        val[base + n] = sgn;
+      }
+      n++;
+    }
+    if (counts) counts[u] = n;
+  }
 }
 
 // Y0 rows: k i.i.d. N(0,1) (Box-Muller on hashed uniforms) normalised to unit L2.

@@ -95,6 +95,7 @@ class NativeALS:
                 raise ValueError("als_create: invalid argument %s" % msg)
             raise ExecutionException("als_create failed: %s %s" % (N.STATUS_NAMES[rc], msg))
         self.n_users = self.n_items = 0
+        self.rank, self.world = 0, 1
 
     def close(self):
         if getattr(self, "h", None):
@@ -183,8 +184,13 @@ class NativeALS:
         return out
 
     def get_interactions(self, by_column=False):
+        from .sharding import local_block
         info = self.info()
-        rows = self.n_items if by_column else self.n_users
+        b, e = local_block(self.n_items if by_column else self.n_users, self.rank, self.world)
+        rows = e - b
+        if self.world > 1:  # shard sizes differ per orientation: go through the slice getter
+            return self.get_interaction_rows(0, rows, by_column=by_column,
+                                             capacity=int(info.nnz) * 4 + 1024)
         ptr = np.empty(rows + 1, dtype=np.int64)
         idx = np.empty(info.nnz, dtype=np.int32)
         val = np.empty(info.nnz, dtype=np.float32)
@@ -252,6 +258,7 @@ class NativeALS:
     def comm_init(self, rank, world_size, unique_id):
         buf = C.create_string_buffer(bytes(unique_id), len(unique_id))
         self.check(self.lib.als_comm_init(self.h, rank, world_size, buf))
+        self.rank, self.world = int(rank), int(world_size)
 
 
 def comm_unique_id():

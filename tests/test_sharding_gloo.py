@@ -1,0 +1,92 @@
+"""world_size-2 `gloo` test (CPU): the host-side sharding of R, the padded block layout of the
+factor replicas and the per-half all-gather reproduce the single-process result bit for bit.
+The per-block arithmetic here is the CPU oracle (this is a test; the product path uses the
+CUDA library and NCCL with the same layout, csrc/als_abi.cu: exchange())."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from conftest import random_problem
+    from oracle import oracle as O
+    from myrrix_recommender_b200 import sharding as S
+    k, U, I = 6, 101, 37  # deliberately not multiples of world
+    ptr, idx, val, Y0 = random_problem(U, I, 7, k, seed=21, neg_fraction=0.1, empty_users=2,
+                                       stale_items=1)
+    tp, ti, tv = O.csr_transpose(ptr, idx, val, I)
+    # this rank's shards of both orientations
+    r_ptr, r_idx, r_val = S.shard_rows(ptr, idx, val, rank, world)
+    c_ptr, c_idx, c_val = S.shard_rows(tp, ti, tv, rank, world)
+    ub, ue = S.local_block(U, rank, world)
+    ib, ie = S.local_block(I, rank, world)
+    bu, bi = S.block_rows(U, world), S.block_rows(I, world)
+    X = np.zeros((S.padded_rows(U, world), k), np.float32)
+    Y = np.zeros((S.padded_rows(I, world), k), np.float32)
+    Y[:I] = Y0
+    for _ in range(3):
+        G = O.transpose_times_self(Y[:I])
+        out = X[ub:ue].copy()
+        O.als_half(r_ptr, r_idx, r_val, Y[:I], G, out)
+        blk = np.zeros((bu, k), np.float32)
+        blk[:ue - ub] = out
+        parts = [torch.zeros(bu, k) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(blk))
+        X = torch.cat(parts).numpy().copy()
+        G = O.transpose_times_self(X[:U])
+        out = Y[ib:ie].copy()
+        O.als_half(c_ptr, c_idx, c_val, X[:U], G, out)
+        blk = np.zeros((bi, k), np.float32)
+        blk[:ie - ib] = out
+        parts = [torch.zeros(bi, k) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(blk))
+        Y = torch.cat(parts).numpy().copy()
+    np.save(os.path.join(out_dir, "x%d.npy" % rank), X[:U])
+    np.save(os.path.join(out_dir, "y%d.npy" % rank), Y[:I])
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_iterations_match_single_process(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    from conftest import random_problem
+    from oracle import oracle as O
+    ptr, idx, val, Y0 = random_problem(101, 37, 7, 6, seed=21, neg_fraction=0.1, empty_users=2,
+                                       stale_items=1)
+    Xo, Yo, _, _ = O.als_run(ptr, idx, val, 37, Y0, max_iterations=3, convergence_threshold=1e-12)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / ("x%d.npy" % r)), Xo)
+        assert np.array_equal(np.load(tmp_path / ("y%d.npy" % r)), Yo)
+
+
+def test_block_layout_helpers():
+    from myrrix_recommender_b200 import sharding as S
+    assert S.block_rows(10, 4) == 3 and S.padded_rows(10, 4) == 12
+    assert [S.local_block(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert S.local_block(2, 3, 4) == (2, 2)  # ranks beyond the data own nothing
+    ptr = np.array([0, 2, 2, 5, 6], np.int64)
+    idx = np.arange(6, dtype=np.int32)
+    val = np.arange(6, dtype=np.float32)
+    p, i, v = S.shard_rows(ptr, idx, val, 1, 2)
+    assert list(p) == [0, 3, 4] and list(i) == [2, 3, 4, 5]
