@@ -252,6 +252,10 @@ def main():
 
     import torch
     import myrrix_recommender_b200 as M
+
+    def dbg(msg):
+        if os.environ.get("BENCH_DEBUG"):
+            print("[rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: no CUDA device visible (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
@@ -274,8 +278,10 @@ def main():
         uid = [M.factorizer.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         als.comm_init(rank, world, uid[0])
+    dbg("comm ready, synthesising")
     als.synth_interactions(U, I, nnz_pu, seed=SEED, neg_fraction=0.0)
     als.synth_y0(seed=SEED)
+    dbg("workload resident")
     h_y0 = None
     if rank == 0 and world == 1 and not args.no_e2e:
         import ctypes as C
@@ -293,6 +299,7 @@ def main():
     # ---- device-resident timing: W warm-up + exactly K timed iterations -----------------
     als.iterate(args.warmup)
     als.sync()
+    dbg("warm-up done")
     als.profile(True)
     als.timings(reset=True)
     sampler = ClockSampler(local_rank)
@@ -304,6 +311,7 @@ def main():
     als.iterate(args.steps)
     ev1.record(stream)
     barrier()
+    dbg("timed region done")
     als.sync()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
@@ -400,8 +408,8 @@ def main():
             item_rows = synth_item_rows(cfg, ni)
             cpu_baseline = cpu_baseline_from_sample(cfg, user_rows, item_rows, h_y0.numpy(),
                                                     h_x.numpy(), "timed once on rank 0")
-    elif rank == 0:
-        als.close()
+    else:
+        als.close()  # every rank: destroying the NCCL communicator is collective
 
     if rank == 0:
         line = {

@@ -213,7 +213,8 @@ int als_comm_unique_id_size(void);
 int als_comm_get_unique_id(void *out_id);
 /* Join a communicator: every rank calls with the same id. After this the handle
  * updates only its own contiguous block of users (X half) / items (Y half) and
- * all-gathers the fresh block over NVLink after each half. */
+ * all-gathers the fresh block over NVLink after each half. unique_id == NULL selects a
+ * partition-only mode (no communicator, no exchange) used to test shard construction. */
 int als_comm_init(als_handle *h, int32_t rank, int32_t world_size, const void *unique_id);
 
 int als_abi_version(void);

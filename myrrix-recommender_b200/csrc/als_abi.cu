@@ -41,7 +41,7 @@ bool load_nccl() {
   if (g_nccl.ok) return true;
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* n : names) {
-    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
     if (g_nccl.lib) break;
   }
   if (!g_nccl.lib) return false;
@@ -357,7 +357,7 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
 }
 
 int exchange(als_handle* h, float* F, long long n_global) {
-  if (h->world == 1) return ALS_OK;
+  if (h->world == 1 || !h->comm) return ALS_OK;
   cudaEvent_t a;
   prof_begin(h, &a);
   const long long b = block_rows(n_global, h->world);
@@ -948,8 +948,15 @@ int als_comm_get_unique_id(void* out_id) {
 }
 
 int als_comm_init(als_handle* h, int32_t rank, int32_t world_size, const void* unique_id) {
-  if (!h || !unique_id || world_size < 1 || rank < 0 || rank >= world_size) return ALS_E_ARG;
+  if (!h || world_size < 1 || rank < 0 || rank >= world_size) return ALS_E_ARG;
   if (h->by_user.ptr) return fail(h, ALS_E_STATE, "als_comm_init must precede als_set_interactions");
+  if (!unique_id) {
+    // Partition-only mode (no communicator): the handle owns block `rank` of `world_size` but
+    // never exchanges factors. Lets one GPU check every rank's shard construction in turn.
+    h->rank = rank;
+    h->world = world_size;
+    return ALS_OK;
+  }
   if (!load_nccl()) return fail(h, ALS_E_NCCL, "libnccl.so.2 not found");
   CU(h, cudaSetDevice(h->device));
   ncclUniqueId id;

@@ -256,7 +256,7 @@ class NativeALS:
         return t
 
     def comm_init(self, rank, world_size, unique_id):
-        buf = C.create_string_buffer(bytes(unique_id), len(unique_id))
+        buf = None if unique_id is None else C.create_string_buffer(bytes(unique_id), len(unique_id))
         self.check(self.lib.als_comm_init(self.h, rank, world_size, buf))
         self.rank, self.world = int(rank), int(world_size)
 

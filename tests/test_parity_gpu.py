@@ -289,3 +289,45 @@ def test_large_config_sampled_row_parity(M, O):
     O.als_half(sp, si, sv, X, G, out)
     fro, mx = rel_err(Y2[rows], out)
     assert fro <= TOL and mx <= TOL, (fro, mx)
+
+
+def test_sharded_synthesis_matches_slices_of_the_whole(M, O):
+    """Partition-only handles (no communicator) on one GPU: every rank's by-user and by-item
+    shard equals the matching slice of the single-GPU matrix, and a sharded half-iteration
+    writes exactly its own block."""
+    from myrrix_recommender_b200 import sharding as S
+    U, I, nnz, k, world = 5003, 701, 23, 32, 3
+    with M.NativeALS(k) as whole:
+        whole.synth_interactions(U, I, nnz, seed=1234567890, neg_fraction=0.05)
+        whole.synth_y0(seed=1234567890)
+        ptr, idx, val = whole.get_interactions()
+        cptr, cidx, cval = whole.get_interactions(by_column=True)
+        Y0 = whole.get_y()
+        whole.half_x(); whole.sync()
+        X_full = whole.get_x()
+        whole.half_y(); whole.sync()
+        Y_full = whole.get_y()
+    for rank in range(world):
+        with M.NativeALS(k) as als:
+            als.comm_init(rank, world, None)
+            als.synth_interactions(U, I, nnz, seed=1234567890, neg_fraction=0.05)
+            als.synth_y0(seed=1234567890)
+            p, i, v = als.get_interactions()
+            ep, ei, ev = S.shard_rows(ptr, idx, val, rank, world)
+            assert np.array_equal(p, ep) and np.array_equal(i, ei) and np.array_equal(v, ev)
+            p, i, v = als.get_interactions(by_column=True)
+            ep, ei, ev = S.shard_rows(cptr, cidx, cval, rank, world)
+            assert np.array_equal(p, ep) and np.array_equal(i, ei) and np.array_equal(v, ev)
+            als.half_x(); als.sync()
+            X = als.get_x()
+            ub, ue = S.local_block(U, rank, world)
+            assert np.array_equal(X[ub:ue], X_full[ub:ue])
+            assert not X[:ub].any() and not X[ue:].any()
+            als.set_x(X_full)  # what the all-gather would deliver
+            als.half_y(); als.sync()
+            Y = als.get_y()
+            ib, ie = S.local_block(I, rank, world)
+            # same arithmetic, but the rhs partial sums are grouped by the CTA's stage stream,
+            # which depends on the row set: equal to fp32 rounding, not bit for bit
+            assert np.allclose(Y[ib:ie], Y_full[ib:ie], rtol=1e-5, atol=1e-6)
+            assert np.array_equal(Y[:ib], Y0[:ib]) and np.array_equal(Y[ie:], Y0[ie:])
