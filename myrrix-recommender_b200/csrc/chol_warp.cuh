@@ -50,35 +50,30 @@ struct CholWarp {
   struct Rows {
     float2 A0[16];   // row `lane`,    columns 0..31
     float2 A1[kP1];  // row `lane+32`, columns 0..63 (KS = 64 only)
+    float diag0, diag1;
   };
 
-  // planes p0 + p1 (shared memory): pair-packed lower triangles whose sum is W_u (G and
-  // lambda*alpha*n_u already folded in by the drain warps).
-  __device__ static __forceinline__ void load(const float* p0, const float* p1, int lane, Rows& R) {
+  // plane (shared memory): pair-packed lower triangle of W_u (G, lambda*alpha*n_u and the unit
+  // diagonal of padding rows already folded in by the drain warps). Also returns this lane's
+  // diagonal entries (for the conditioning check).
+  __device__ static __forceinline__ void load(const float* pl, int lane, Rows& R) {
 #pragma unroll
     for (int P = 0; P < 16; P++) {
       float2 v = make_float2(0.f, 0.f);
-      if (lane >= 2 * P) {
-        const int o = offP(P) + 2 * (lane - 2 * P);
-        const float2 a = *reinterpret_cast<const float2*>(p0 + o);
-        const float2 c = *reinterpret_cast<const float2*>(p1 + o);
-        v = make_float2(a.x + c.x, a.y + c.y);
-      }
+      if (lane >= 2 * P) v = *reinterpret_cast<const float2*>(pl + offP(P) + 2 * (lane - 2 * P));
       R.A0[P] = v;
     }
     if (kTwoRows) {
 #pragma unroll
       for (int P = 0; P < 32; P++) {
         float2 v = make_float2(0.f, 0.f);
-        if (lane + 32 >= 2 * P) {
-          const int o = offP(P) + 2 * (lane + 32 - 2 * P);
-          const float2 a = *reinterpret_cast<const float2*>(p0 + o);
-          const float2 c = *reinterpret_cast<const float2*>(p1 + o);
-          v = make_float2(a.x + c.x, a.y + c.y);
-        }
+        if (lane + 32 >= 2 * P) v = *reinterpret_cast<const float2*>(pl + offP(P) + 2 * (lane + 32 - 2 * P));
         R.A1[P] = v;
       }
     }
+    // diagonal entries of my rows: element (r, r) lives in pair r/2, slot r&1
+    R.diag0 = pl[offP(lane >> 1) + 2 * (lane - (lane & ~1)) + (lane & 1)];
+    R.diag1 = kTwoRows ? pl[offP((lane + 32) >> 1) + 2 * ((lane + 32) - ((lane + 32) & ~1)) + (lane & 1)] : 0.f;
   }
 
   template <int N>
@@ -112,15 +107,8 @@ struct CholWarp {
     // largest diagonal entry (for the conditioning check)
     float dmax;
     {
-      float mine = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; j++)
-        if (j == lane && j < k) mine = (j & 1) ? A0[j >> 1].y : A0[j >> 1].x;
-      if (kTwoRows) {
-#pragma unroll
-        for (int j = 32; j < 64; j++)
-          if (j == lane + 32 && j < k) mine = fmaxf(mine, (j & 1) ? A1[j >> 1].y : A1[j >> 1].x);
-      }
+      float mine = (lane < k) ? R.diag0 : 0.f;
+      if (kTwoRows && lane + 32 < k) mine = fmaxf(mine, R.diag1);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mine = fmaxf(mine, __shfl_xor_sync(FULL, mine, o));
       dmax = mine;

@@ -46,7 +46,7 @@ constexpr int kMmaWarp = kFirstProd + kProdWarps;            // warp 19 (shares 
 constexpr int kThreads = (kMmaWarp + 1) * 32;                // 640: 5 warps per SM sub-partition
 constexpr int kStages = 16;                                  // operand ring depth (4 KB each)
 constexpr int kAccSlots = 4;                                 // TMEM accumulators in flight
-constexpr int kWSlots = 4;                                   // W slots (drain -> Cholesky)
+constexpr int kWSlots = 8;                                   // W slots (drain -> Cholesky), one per Cholesky warp
 constexpr int kBSlots = 8;                                   // rhs ring depth (== kCholWarps)
 static_assert(kBSlots == kCholWarps && kCholWarps % kWSlots == 0, "ring/consumer phase bookkeeping");
 constexpr int kSegStages = 64;                               // stages per accumulation segment
@@ -56,6 +56,7 @@ constexpr int kTmemCols = 512;
 // Cholesky and 2 producer/MMA warps and setmaxnreg re-balances within 5 x 96 x 32 = 15360:
 constexpr int kRegsProd = 88, kRegsDrain = 48, kRegsChol = 128;
 static_assert(32 * (2 * kRegsProd + kRegsDrain + 2 * kRegsChol) <= 5 * 96 * 32, "register pool");
+constexpr bool kCholLockstep = true;   // all Cholesky warps enter each sweep together
 constexpr float kCondLimit = 256.f;  // max diag / min pivot above which a row goes to fp64
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -64,8 +65,8 @@ struct Smem {
   using CW = CholWarp<KS>;
   static constexpr size_t kRing = (size_t)kStages * 4096 + 2048;  // +pad: KS=32 A-operand overrun
   static constexpr size_t kPlaneBytes = sizeof(float) * ((CW::kPlane + 3) / 4 * 4);
-  static constexpr size_t off_planes = kRing;                                   // [kWSlots][2]
-  static constexpr size_t off_g32 = off_planes + kWSlots * 2 * kPlaneBytes;
+  static constexpr size_t off_planes = kRing;                                   // [kWSlots]
+  static constexpr size_t off_g32 = off_planes + kWSlots * kPlaneBytes;
   static constexpr size_t off_bpart = off_g32 + kPlaneBytes;                    // [kBSlots][P][KS]
   static constexpr size_t off_colbuf = off_bpart + sizeof(float) * kBSlots * kProdWarps * KS;
   static constexpr size_t off_bars = off_colbuf + sizeof(float) * kCholWarps * CW::kScratch;
@@ -353,17 +354,18 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
         const int nst = (cnt + E - 1) / E;
         const int nseg = (nst + kSegStages - 1) / kSegStages;
         const int ws = useq % kWSlots;
-        float* plane = planes + (ws * 2 + (is_lo ? 1 : 0)) * kPlaneF;
+        float* plane = planes + ws * kPlaneF;
         const float lam_n = (float)(p.lambda_alpha * (double)cnt);
-        if (useq >= kWSlots) {  // slot last held row useq - kWSlots: wait until it was loaded
-          const int prev = useq - kWSlots;
-          mbar_wait_id(&w_empty[prev % kCholWarps], (uint32_t)((prev / kCholWarps) & 1), 4);
-        }
+        // slot ws last held row useq - kWSlots, consumed by the same Cholesky warp
+        mbar_wait_id(&w_empty[ws], (uint32_t)(((useq / kWSlots) & 1) ^ 1), 4);
         for (int seg = 0; seg < nseg; seg++, gseg++) {
           const int a = (int)(gseg % kAccSlots);
           mbar_wait_id(&acc_full[a], (gseg / kAccSlots) & 1, 5);
           tc_fence_after_sync();
           const uint32_t taddr = tmem_base + lane_base + (uint32_t)(a * G::kN);
+          // hi-row warps write (W = G + lambda*alpha*n_u*I + hi part), then the lo-row warps add
+          // their part: one warpgroup barrier between the two (whole warps are hi or lo)
+          if (!is_hi) bar_sync(2, 128);
 #pragma unroll 1
           for (int jc = 0; jc < KS / 16; jc++) {
             if (jc * 16 > warp_max_row) break;  // chunk entirely above the diagonal for this warp
@@ -381,13 +383,12 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
                   v.y = (i > j) ? __uint_as_float(v0[jj + 1]) + __uint_as_float(v1[jj + 1]) : 0.f;
                   const int P = j >> 1;
                   const int o = 2 * (KS * P - P * (P - 1)) + 2 * (i - j);
-                  if (seg == 0) {
-                    // W = G + lambda*alpha*n_u*I + ... (ALS.java:447-450, 488-492): hi plane only
-                    if (is_hi) {
-                      const float2 g = *reinterpret_cast<const float2*>(g32 + o);
-                      v.x += g.x + ((i == j && i < k) ? lam_n : 0.f);
-                      v.y += g.y + ((i == j + 1 && i < k) ? lam_n : 0.f);
-                    }
+                  if (is_hi && seg == 0) {
+                    // W = G + lambda*alpha*n_u*I + ... (ALS.java:447-450, 488-492); padding rows
+                    // (i >= k) get a unit diagonal so the factorisation stays finite
+                    const float2 g = *reinterpret_cast<const float2*>(g32 + o);
+                    v.x += g.x + ((i == j) ? (i < k ? lam_n : 1.f) : 0.f);
+                    v.y += g.y + ((i == j + 1) ? (i < k ? lam_n : 1.f) : 0.f);
                   } else {
                     const float2 old = *reinterpret_cast<const float2*>(plane + o);
                     v.x += old.x;
@@ -400,8 +401,10 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
           }
           tc_fence_before_sync();
           mbar_arrive(&acc_empty[a]);  // accumulator may be overwritten by the next segment
+          if (is_hi) bar_sync(2, 128);    // releases the lo-row warps of this segment
+          if (seg + 1 < nseg) bar_sync(3, 128);  // next segment's hi pass reads what lo wrote
         }
-        mbar_arrive(&w_full[useq % kCholWarps]);  // 128 arrivals: both planes of this row complete
+        mbar_arrive(&w_full[ws]);  // 128 arrivals: the plane of this row is complete
         useq++;
       }
     }
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
         const int ws = useq % kWSlots;
         mbar_wait_id(&w_full[cw], (uint32_t)((useq / kCholWarps) & 1), 6);
         typename CW::Rows R;
-        CW::load(planes + (ws * 2) * kPlaneF, planes + (ws * 2 + 1) * kPlaneF, lane, R);
+        CW::load(planes + ws * kPlaneF, lane, R);
         __syncwarp();
         if (lane == 0) mbar_arrive(&w_empty[cw]);  // slot free: the row now lives in registers
         mbar_wait_id(&b_full[cw], (uint32_t)((useq / kBSlots) & 1), 7);
@@ -440,21 +443,9 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&b_empty[cw]);
-        // padding rows (k < KS) have a zero diagonal: give them a unit pivot so the sweep stays
-        // finite; their solution entries are exactly 0 and are never written.
-        if (k < KS) {
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (j == lane && j >= k) { if (j & 1) R.A0[j >> 1].y = 1.f; else R.A0[j >> 1].x = 1.f; }
-          if (KS == 64) {
-#pragma unroll
-            for (int j = 32; j < 64; j++)
-              if (j == lane + 32 && j >= k) { if (j & 1) R.A1[j >> 1].y = 1.f; else R.A1[j >> 1].x = 1.f; }
-          }
-        }
         // All Cholesky warps enter the sweep together: they then run the same instruction
         // stream in near lockstep, so the instruction cache sees one stream instead of eight.
-        bar_sync(1, kCholWarps * 32);
+        if (kCholLockstep) bar_sync(1, kCholWarps * 32);
         float x0, x1;
         const bool ok = CW::factor_solve(R, scratch, b0, b1, p.threshold, kCondLimit, lane, k, x0, x1);
         if (ok) {
@@ -469,7 +460,8 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
       }
     }
     // tail: warps without a row in the last round still meet the others at the barrier
-    if ((useq % kCholWarps) != 0 && cw >= (useq % kCholWarps)) bar_sync(1, kCholWarps * 32);
+    if (kCholLockstep && (useq % kCholWarps) != 0 && cw >= (useq % kCholWarps))
+      bar_sync(1, kCholWarps * 32);
   }
 
   tc_fence_before_sync();
