@@ -1,26 +1,30 @@
 // chol_warp.cuh -- one warp factorises and solves one k x k SPD system entirely in
 // registers (fp32), k = KS in {32, 64}.
 //
-// Row distribution: lane l owns row l (and row l+32 when KS = 64); a row lives in
-// registers as float2 pairs along the column index.  Panel-blocked right-looking LDL^T,
-// 8 columns per block, block loop is a REAL loop (compact code: the four roles of the
-// row-update kernel must share the instruction cache) made possible by rotating each row's
-// register array by 4 pairs per block so the active panel always sits at positions 0..3:
-//   1. eight cheap in-panel steps: the 8 owner lanes of rows jb..jb+7 publish their entry of
-//      column j (10 floats incl. pivot and z_j), every lane scales its own entry and updates
-//      only the panel columns of its rows; the forward substitution z = L^{-1} b rides along;
-//   2. every lane publishes the unscaled panel entries u_c[t] of its rows (transposed:
-//      Ut[t][c]), then one rank-8 update   W[i][c] -= sum_t L[i][jb+t] * u_c[t]   of all
-//      columns right of the panel: 16-byte broadcast loads + packed fp32x2 FMAs, whole
-//      8-column groups at a time (finished groups skipped by a warp-uniform test).
-// D^{-1} is lane-local; the backward substitution x = L^{-T} y runs block-wise with warp
-// all-reduces for the part below the block and an 8x8 unit-triangular solve inside it.
+// Row distribution: lane l owns row l (and row l+32 when KS = 64); a row lives in registers
+// as float2 pairs along the column index, every index static (the sweep is fully unrolled).
+//
+// Forward sweep (right-looking LDL^T, one column per step, KS steps):
+//   every lane publishes its entries of column j (u[i] = W[i][j]) into a double-buffered
+//   KS-float vector in shared memory, the owner of row j adds the pivot d_j and the rhs entry
+//   z_j; one __syncwarp; every lane then reads (d_j, z_j), forms L[i][j] = u[i]/d_j for its own
+//   rows (kept in place of W[i][j]), folds the forward substitution b_i -= L[i][j] z_j, and
+//   updates its rows right of column j with 16-byte broadcast loads of u and packed fp32x2
+//   FMAs:  W[i][c] -= L[i][j] * u[c].  Rows at or above the pivot use a zero multiplier, so
+//   entries above the diagonal may hold anything and are never read.
+// Backward sweep (x = L^-T D^-1 z), eight columns per block from the last block up:
+//   rows below the block contribute  sum_i L[i][jb+t] x_i  (packed FMAs, then a transposing
+//   butterfly: 9 shuffles reduce 8 sums over 32 lanes), the 8x8 unit-triangular solve inside
+//   the block runs redundantly on every lane with the block's L entries read back from a
+//   small shared-memory copy written during the forward sweep (no dependent shuffles).
 //
 // This is the fast path of MatrixUtils.getSolver(Wu).solveDToF(b) (ALS.java:494): rows whose
 // pivots indicate a singular or ill-conditioned W_u (max diag / min pivot > cond_limit, or
 // a pivot <= threshold / non-finite) are NOT solved here; the caller re-solves them in fp64
 // (row_update_simt.cuh), which also raises ALS_E_SINGULAR exactly as before.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace als {
@@ -30,6 +34,20 @@ __device__ __forceinline__ float fast_rcp(float d) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
   return r * fmaf(-d, r, 2.0f);  // one Newton step: ~1 ulp
 }
+
+// Compile-time loop: f(integral_constant<int, J>) for J = BEGIN, BEGIN+STEP, ... (END exclusive).
+// (#pragma unroll gives up on bodies this large and would demote the register rows to
+// local memory.)
+template <int J, int END, int STEP = 1>
+struct StaticFor {
+  template <class F>
+  __device__ static __forceinline__ void run(F&& f) {
+    if constexpr ((STEP > 0) ? (J < END) : (J > END)) {
+      f(std::integral_constant<int, J>{});
+      StaticFor<J + STEP, END, STEP>::run(f);
+    }
+  }
+};
 
 template <int KS>
 struct CholWarp {
@@ -41,10 +59,11 @@ struct CholWarp {
   // 8-byte words: conflict-free for both the drain's stores and the Cholesky warp's loads.
   static constexpr int kPlane = KS * KS / 2 + KS;
   static constexpr int kBlocks = KS / 8;
-  static constexpr int kP1 = kTwoRows ? 32 : 4;  // pairs in row lane+32 (dummy 4 for KS=32)
-  // per-warp scratch: 2 step buffers of 12 floats (8 column entries, z_j, d_j) + Ut[8][KS] + Lt[8][KS]
-  static constexpr int kStepBuf = 12;
-  static constexpr int kScratch = 2 * kStepBuf + 16 * KS;  // floats, 16-byte multiple
+  static constexpr int kP1 = kTwoRows ? 32 : 1;  // pairs in row lane+32 (dummy for KS=32)
+  // per-warp scratch: 2 column buffers of KS entries + (d_j, z_j) + pad, then the 8x8 diagonal
+  // blocks of L (row-major, one per block of 8 columns)
+  static constexpr int kUBuf = KS + 4;
+  static constexpr int kScratch = 2 * kUBuf + kBlocks * 64;  // floats, 16-byte multiple
   __host__ __device__ static constexpr int offP(int P) { return 2 * (KS * P - P * (P - 1)); }
 
   struct Rows {
@@ -63,32 +82,40 @@ struct CholWarp {
       if (lane >= 2 * P) v = *reinterpret_cast<const float2*>(pl + offP(P) + 2 * (lane - 2 * P));
       R.A0[P] = v;
     }
-    if (kTwoRows) {
+    if constexpr (kTwoRows) {
 #pragma unroll
       for (int P = 0; P < 32; P++) {
         float2 v = make_float2(0.f, 0.f);
         if (lane + 32 >= 2 * P) v = *reinterpret_cast<const float2*>(pl + offP(P) + 2 * (lane + 32 - 2 * P));
         R.A1[P] = v;
       }
+    } else {
+      R.A1[0] = make_float2(0.f, 0.f);
     }
     // diagonal entries of my rows: element (r, r) lives in pair r/2, slot r&1
     R.diag0 = pl[offP(lane >> 1) + 2 * (lane - (lane & ~1)) + (lane & 1)];
     R.diag1 = kTwoRows ? pl[offP((lane + 32) >> 1) + 2 * ((lane + 32) - ((lane + 32) & ~1)) + (lane & 1)] : 0.f;
   }
 
+  // element c of a pair-packed register row (c static after unrolling; clamped so dead
+  // instantiations never index out of bounds)
   template <int N>
-  __device__ static __forceinline__ void rotate_left4(float2 (&A)[N]) {
-    const float2 t0 = A[0], t1 = A[1], t2 = A[2], t3 = A[3];
-#pragma unroll
-    for (int P = 0; P + 4 < N; P++) A[P] = A[P + 4];
-    A[N - 4] = t0; A[N - 3] = t1; A[N - 2] = t2; A[N - 1] = t3;
+  __device__ static __forceinline__ float get(const float2 (&A)[N], int c) {
+    const int p = (c >> 1) < N ? (c >> 1) : 0;
+    return (c & 1) ? A[p].y : A[p].x;
   }
   template <int N>
-  __device__ static __forceinline__ void rotate_right4(float2 (&A)[N]) {
-    const float2 t0 = A[N - 4], t1 = A[N - 3], t2 = A[N - 2], t3 = A[N - 1];
-#pragma unroll
-    for (int P = N - 1; P >= 4; P--) A[P] = A[P - 4];
-    A[0] = t0; A[1] = t1; A[2] = t2; A[3] = t3;
+  __device__ static __forceinline__ void set(float2 (&A)[N], int c, float v) {
+    const int p = (c >> 1) < N ? (c >> 1) : 0;
+    if (c & 1) A[p].y = v; else A[p].x = v;
+  }
+  // pair p of the row: W[.][2p..2p+1] -= m * (u.x, u.y) for the columns right of column j
+  template <int N>
+  __device__ static __forceinline__ void update_pair(float2 (&A)[N], int p, int j, float m, float2 nm,
+                                                     float2 u) {
+    if (p >= N || 2 * p + 1 <= j) return;             // pair finished (or outside this row)
+    if (2 * p == j) A[p].y = fmaf(-m, u.y, A[p].y);   // .x is column j itself: now holds L[i][j]
+    else A[p] = ffma2(nm, u, A[p]);
   }
 
   // scratch: kScratch floats of shared memory private to this warp. b0/b1: rhs entries of
@@ -101,8 +128,7 @@ struct CholWarp {
     constexpr unsigned FULL = 0xffffffffu;
     float2 (&A0)[16] = R.A0;
     float2 (&A1)[kP1] = R.A1;
-    float* Ut = scratch + 2 * kStepBuf;  // [8][KS] unscaled panel entries, transposed
-    float* Lt = Ut + 8 * KS;             // [8][KS] L panel entries, transposed
+    float* Ld = scratch + 2 * kUBuf;  // [kBlocks][8][8] diagonal blocks of L
 
     // largest diagonal entry (for the conditioning check)
     float dmax;
@@ -114,175 +140,153 @@ struct CholWarp {
       dmax = mine;
     }
     float inv0 = 0.f, inv1 = 0.f;  // 1/d of my rows
-    float d0 = dmax, d1 = dmax;    // pivots of my rows (judged after the sweep)
 
-#pragma unroll
-    for (int b = 0; b < kBlocks; b++) {
-      const int jb = 8 * b;
-      const bool a0_live = jb < 32;     // row `lane` still has unfinished columns
-      const bool own_in0 = jb < 32;     // the panel's diagonal rows jb..jb+7 live in A0 (else A1)
-      const int tl = lane - (jb & 31);  // 0..7 on the lanes owning rows jb..jb+7
-      const bool owner = tl >= 0 && tl < 8;
-      // ---- 1. eight in-panel steps, two per trip; the panel's 4 pairs rotate by one pair per
-      //         trip so the active pair is always position 0 (compact code) ------------------
-#pragma unroll 1
-      for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int t = 2 * r + h;
-          const int j = jb + t;
-          float* sb = scratch + h * kStepBuf;
-          const float w0 = h ? A0[0].y : A0[0].x;
-          const float w1 = kTwoRows ? (h ? A1[0].y : A1[0].x) : 0.f;
-          if (owner) {
-            const float mine = own_in0 ? w0 : w1;
-            // slot of panel row tl in the rotated frame; rows <= j contribute zeros
-            sb[(tl - 2 * r) & 7] = (tl > t) ? mine : 0.f;
-            if (tl == t) {
-              sb[8] = own_in0 ? b0 : b1;  // z_j (unit-lower L)
-              sb[9] = mine;               // pivot d_j
-            }
-          }
-          __syncwarp();
-          const float4 qa = *reinterpret_cast<const float4*>(sb);
-          const float4 qb = *reinterpret_cast<const float4*>(sb + 4);
-          const float2 zd = *reinterpret_cast<const float2*>(sb + 8);
-          const float zj = zd.x, d = zd.y;
-          const float inv = fast_rcp(d);
-          const float m0 = a0_live ? w0 * inv : 0.f;
-          const float m1 = w1 * inv;  // L[i][j]
-          if (tl == t) { if (own_in0) { inv0 = inv; d0 = d; } else { inv1 = inv; d1 = d; } }
-          // forward substitution: b_i -= L[i][j] * z_j for rows below j
-          if (a0_live && lane > j) b0 = fmaf(-m0, zj, b0);
-          if (kTwoRows && lane + 32 > j) b1 = fmaf(-m1, zj, b1);
-          // update the panel columns of my rows (zeros in sb leave finished columns alone)
-          const float2 c0 = make_float2(qa.x, qa.y), c1 = make_float2(qa.z, qa.w);
-          const float2 c2 = make_float2(qb.x, qb.y), c3 = make_float2(qb.z, qb.w);
-          if (a0_live) {
-            const float2 nm0 = make_float2(-m0, -m0);
-            A0[0] = ffma2(nm0, c0, A0[0]); A0[1] = ffma2(nm0, c1, A0[1]);
-            A0[2] = ffma2(nm0, c2, A0[2]); A0[3] = ffma2(nm0, c3, A0[3]);
-          }
-          if (kTwoRows) {
-            const float2 nm1 = make_float2(-m1, -m1);
-            A1[0] = ffma2(nm1, c0, A1[0]); A1[1] = ffma2(nm1, c1, A1[1]);
-            A1[2] = ffma2(nm1, c2, A1[2]); A1[3] = ffma2(nm1, c3, A1[3]);
-          }
-          // publish for the rank-8 update: the unscaled entry u_c[t] of my rows (rows inside or
-          // above the panel publish 0) and L[i][j]; keep L[i][j] in place of the entry
-          if (a0_live) {
-            Ut[t * KS + lane] = (lane >= jb + 8) ? w0 : 0.f;
-            Lt[t * KS + lane] = m0;
-            if (h) A0[0].y = m0; else A0[0].x = m0;
-          }
-          if (kTwoRows) {
-            Ut[t * KS + lane + 32] = (lane + 32 >= jb + 8) ? w1 : 0.f;
-            Lt[t * KS + lane + 32] = m1;
-            if (h) A1[0].y = m1; else A1[0].x = m1;
-          }
-        }
-        // rotate the panel pairs by one
-        if (a0_live) { const float2 t0 = A0[0]; A0[0] = A0[1]; A0[1] = A0[2]; A0[2] = A0[3]; A0[3] = t0; }
-        if (kTwoRows) { const float2 t1 = A1[0]; A1[0] = A1[1]; A1[1] = A1[2]; A1[2] = A1[3]; A1[3] = t1; }
-      }
+    // ---- forward sweep ----------------------------------------------------------------------
+    StaticFor<0, KS>::run([&](auto jc) {
+      constexpr int j = decltype(jc)::value;
+      float* buf = scratch + (j & 1) * kUBuf;
+      constexpr bool piv0 = j < 32;  // the pivot row lives in A0 (else in A1)
+      constexpr int own = j & 31;    // lane that owns row j
+      const float w0 = piv0 ? get(A0, j) : 0.f;
+      const float w1 = kTwoRows ? get(A1, j) : 0.f;
+      if (piv0) buf[lane] = w0;
+      if (kTwoRows) buf[32 + lane] = w1;
+      if (lane == own)
+        *reinterpret_cast<float2*>(buf + KS) = piv0 ? make_float2(w0, b0) : make_float2(w1, b1);
       __syncwarp();
-      // ---- 2. rank-8 update of the columns right of the panel ------------------------------
-      const int groups = kBlocks - b;  // live 8-column groups incl. the panel itself (g = 0)
-      if (groups > 1) {
-#pragma unroll 1
-        for (int t = 0; t < 8; t++) {
-          const float l0 = a0_live ? Lt[t * KS + lane] : 0.f;
-          const float l1 = kTwoRows ? Lt[t * KS + lane + 32] : 0.f;
-          const float2 nl0 = make_float2(-l0, -l0), nl1 = make_float2(-l1, -l1);
-          const float* ut = Ut + t * KS + jb;
+      const float2 dz = *reinterpret_cast<const float2*>(buf + KS);  // pivot d_j, rhs z_j
+      const float inv = fast_rcp(dz.x);
+      float m0 = 0.f, m1 = 0.f;  // L[i][j] of my rows; 0 for rows at or above the pivot
+      if (piv0) {
+        m0 = (lane > own) ? w0 * inv : 0.f;
+        if (lane == own) inv0 = inv;
+        if (kTwoRows) m1 = w1 * inv;
+        b0 = fmaf(-m0, dz.y, b0);
+        set(A0, j, m0);
+      } else {
+        m1 = (lane > own) ? w1 * inv : 0.f;
+        if (lane == own) inv1 = inv;
+      }
+      if (kTwoRows) {
+        b1 = fmaf(-m1, dz.y, b1);
+        set(A1, j, m1);
+      }
+      const float2 nm0 = make_float2(-m0, -m0), nm1 = make_float2(-m1, -m1);
 #pragma unroll
-          for (int g = 1; g < kBlocks; g++) {
-            if (g < groups) {  // warp-uniform
-              const float4 qa = *reinterpret_cast<const float4*>(ut + 8 * g);
-              const float4 qb = *reinterpret_cast<const float4*>(ut + 8 * g + 4);
-              const float2 c0 = make_float2(qa.x, qa.y), c1 = make_float2(qa.z, qa.w);
-              const float2 c2 = make_float2(qb.x, qb.y), c3 = make_float2(qb.z, qb.w);
-              if (kTwoRows) {
-                A1[4 * g + 0] = ffma2(nl1, c0, A1[4 * g + 0]);
-                A1[4 * g + 1] = ffma2(nl1, c1, A1[4 * g + 1]);
-                A1[4 * g + 2] = ffma2(nl1, c2, A1[4 * g + 2]);
-                A1[4 * g + 3] = ffma2(nl1, c3, A1[4 * g + 3]);
-              }
-              if (g < 4 && jb + 8 * g < 32) {  // row `lane` has only columns 0..31 (warp-uniform)
-                A0[4 * g + 0] = ffma2(nl0, c0, A0[4 * g + 0]);
-                A0[4 * g + 1] = ffma2(nl0, c1, A0[4 * g + 1]);
-                A0[4 * g + 2] = ffma2(nl0, c2, A0[4 * g + 2]);
-                A0[4 * g + 3] = ffma2(nl0, c3, A0[4 * g + 3]);
-              }
-            }
-          }
+      for (int q = (j + 1) / 4; q < KS / 4; q++) {
+        const float4 u = *reinterpret_cast<const float4*>(buf + 4 * q);
+        const float2 ua = make_float2(u.x, u.y), ub = make_float2(u.z, u.w);
+        if (kTwoRows) {
+          update_pair(A1, 2 * q, j, m1, nm1, ua);
+          update_pair(A1, 2 * q + 1, j, m1, nm1, ub);
+        }
+        if (piv0) {
+          update_pair(A0, 2 * q, j, m0, nm0, ua);
+          update_pair(A0, 2 * q + 1, j, m0, nm0, ub);
         }
       }
-      __syncwarp();  // Ut / Lt are rewritten by the next block
-      // rotate so the next panel sits at positions 0..3 (finished L goes to the end)
-      if (kTwoRows) rotate_left4(A1);
-      if (a0_live) rotate_left4(A0);
-    }
-    // judge the pivots: smallest pivot vs threshold / largest diagonal entry
-    float dmin;
+      if ((j & 7) == 7) {
+        // keep the finished 8x8 diagonal block of L for the backward sweep: the eight lanes
+        // owning rows jb..jb+7 write their in-block entries (entries right of the diagonal are
+        // never read back)
+        const int jb = j - 7;
+        if ((lane >> 3) == ((jb & 31) >> 3)) {
+          float* dst = Ld + (j >> 3) * 64 + (lane & 7) * 8;
+          float4 lo, hi;
+          if (piv0) {
+            lo = make_float4(get(A0, jb), get(A0, jb + 1), get(A0, jb + 2), get(A0, jb + 3));
+            hi = make_float4(get(A0, jb + 4), get(A0, jb + 5), get(A0, jb + 6), get(A0, jb + 7));
+          } else {
+            lo = make_float4(get(A1, jb), get(A1, jb + 1), get(A1, jb + 2), get(A1, jb + 3));
+            hi = make_float4(get(A1, jb + 4), get(A1, jb + 5), get(A1, jb + 6), get(A1, jb + 7));
+          }
+          *reinterpret_cast<float4*>(dst) = lo;
+          *reinterpret_cast<float4*>(dst + 4) = hi;
+        }
+      }
+    });
+    // Judge the pivots of the true rows through their reciprocals (each lane kept 1/d of its
+    // own rows): d > threshold  <=>  0 < 1/d < 1/threshold, and d * cond_limit >= dmax  <=>
+    // dmax / d <= cond_limit.  Zero, negative and NaN pivots fail the first test.  No early
+    // exit: the backward sweep runs regardless, so the warp provably stays converged.
+    bool good = dmax > threshold && isfinite(dmax);
     {
-      float mine = dmax;
-      if (lane < k) mine = fminf(mine, d0);
-      if (kTwoRows && lane + 32 < k) mine = fminf(mine, d1);
-      bool fin = isfinite(d0) && isfinite(d1) && isfinite(inv0) && isfinite(inv1);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mine = fminf(mine, __shfl_xor_sync(FULL, mine, o));
-      dmin = __all_sync(FULL, fin) ? mine : -1.f;
+      const float inv_t = 1.0f / threshold;
+      if (lane < k) good = good && inv0 > 0.f && inv0 < inv_t && inv0 * dmax <= cond_limit;
+      if (kTwoRows && lane + 32 < k) good = good && inv1 > 0.f && inv1 < inv_t && inv1 * dmax <= cond_limit;
     }
-    const bool bad = !(dmax > threshold) || !isfinite(dmax) || !(dmin > threshold);
-    // after KS/8 rotations of A1 (32 pairs, 8 blocks) and 4 of A0 (16 pairs) both arrays are
-    // back in natural column order and hold L (unit lower, strictly below the diagonal).
-    if (bad || !(dmin * cond_limit >= dmax)) return false;
+    __syncwarp();  // diagonal blocks visible to every lane
 
     // ---- y = D^{-1} z, then x = L^{-T} y, block-wise from the last block ---------------------
     x0 = b0 * inv0;
     x1 = kTwoRows ? b1 * inv1 : 0.f;
+    const bool k4 = (lane & 4) != 0, k2 = (lane & 2) != 0, k1 = (lane & 1) != 0;
+    StaticFor<kBlocks - 1, -1, -1>::run([&](auto bc) {
+      constexpr int b = decltype(bc)::value;
+      constexpr int jb = 8 * b;
+      constexpr bool in0 = jb < 32;               // the block's rows live in A0/x0 (else A1/x1)
+      constexpr int grp = (jb & 31) >> 3;         // lanes 8*grp .. 8*grp+7 own rows jb..jb+7
+      const bool mine = (lane >> 3) == grp;
+      const float y = in0 ? x0 : x1;          // y_{jb + (lane & 7)} on the owner lanes
+      float v;                                // y_j - sum_{i >= jb+8} L[i][j] x_i for j = jb + (lane & 7)
+      if (jb + 8 < KS) {
+        float2 acc[4];
 #pragma unroll
-    for (int b = kBlocks - 1; b >= 0; b--) {
-      const int jb = 8 * b;
-      const bool in0 = jb < 32;  // the block's rows live in A0/x0 (else A1/x1)
-      if (kTwoRows) rotate_right4(A1);
-      if (in0) rotate_right4(A0);
-      // s[t] = y_j - sum over rows i >= jb+8 of L[i][j] x_i   (j = jb+t), all-reduced
+        for (int q = 0; q < 4; q++) acc[q] = make_float2(0.f, 0.f);
+        if (kTwoRows) {
+          float xm = x1;                      // rows lane+32 >= jb+8 only
+          if (jb + 8 > 32) xm = (lane + 32 >= jb + 8) ? x1 : 0.f;
+          const float2 xx = make_float2(xm, xm);
+#pragma unroll
+          for (int q = 0; q < 4; q++) acc[q] = ffma2(A1[(jb / 2 + q) < kP1 ? (jb / 2 + q) : 0], xx, acc[q]);
+        }
+        if (jb + 8 < 32) {
+          const float xm = (lane >= jb + 8) ? x0 : 0.f;
+          const float2 xx = make_float2(xm, xm);
+#pragma unroll
+          for (int q = 0; q < 4; q++) acc[q] = ffma2(A0[(jb / 2 + q) & 15], xx, acc[q]);
+        }
+        // transposing butterfly: after the xor-4/2/1 rounds a lane holds the sum for
+        // t = lane & 7 over its group of 8 lanes; xor-8/16 finish it over the warp
+        const float s0 = acc[0].x, s1 = acc[0].y, s2 = acc[1].x, s3 = acc[1].y;
+        const float s4 = acc[2].x, s5 = acc[2].y, s6 = acc[3].x, s7 = acc[3].y;
+        const float r0 = (k4 ? s4 : s0) + __shfl_xor_sync(FULL, k4 ? s0 : s4, 4);
+        const float r1 = (k4 ? s5 : s1) + __shfl_xor_sync(FULL, k4 ? s1 : s5, 4);
+        const float r2 = (k4 ? s6 : s2) + __shfl_xor_sync(FULL, k4 ? s2 : s6, 4);
+        const float r3 = (k4 ? s7 : s3) + __shfl_xor_sync(FULL, k4 ? s3 : s7, 4);
+        const float q0 = (k2 ? r2 : r0) + __shfl_xor_sync(FULL, k2 ? r0 : r2, 2);
+        const float q1 = (k2 ? r3 : r1) + __shfl_xor_sync(FULL, k2 ? r1 : r3, 2);
+        float p = (k1 ? q1 : q0) + __shfl_xor_sync(FULL, k1 ? q0 : q1, 1);
+        p = mine ? y - p : -p;
+        p += __shfl_xor_sync(FULL, p, 8);
+        p += __shfl_xor_sync(FULL, p, 16);
+        v = p;
+      } else {
+        v = y;  // last block: nothing below it
+      }
       float s[8];
 #pragma unroll
-      for (int t = 0; t < 8; t++) {
-        const int j = jb + t;
-        float part = 0.f;
-        if (in0 && lane >= jb + 8) part = ((t & 1) ? A0[t >> 1].y : A0[t >> 1].x) * x0;
-        if (kTwoRows && lane + 32 >= jb + 8)
-          part = fmaf((t & 1) ? A1[t >> 1].y : A1[t >> 1].x, x1, part);
-        part = -part;
-        if (lane == (j & 31)) part += in0 ? x0 : x1;  // + y_j from its owner
-        s[t] = part;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int t = 0; t < 8; t++) s[t] += __shfl_xor_sync(FULL, s[t], o);
-      }
+      for (int t = 0; t < 8; t++) s[t] = __shfl_sync(FULL, v, (jb + 8 < KS) ? t : 8 * grp + t);
       // in-block unit-upper-triangular solve, redundantly on every lane:
-      // x_j = s_j - sum_{t' > t} L[jb+t'][jb+t] x_{jb+t'}; L[jb+t'][.] sits in lane (jb+t')&31
+      // x_{jb+t} = s_t - sum_{t' > t} L[jb+t'][jb+t] x_{jb+t'}
+      const float* Lb = Ld + b * 64;
 #pragma unroll
-      for (int t = 6; t >= 0; t--) {
-        const float mine = in0 ? ((t & 1) ? A0[t >> 1].y : A0[t >> 1].x)
-                               : (kTwoRows ? ((t & 1) ? A1[t >> 1].y : A1[t >> 1].x) : 0.f);
-#pragma unroll
-        for (int tp = 7; tp > t; tp--) {
-          const float l = __shfl_sync(FULL, mine, (jb + tp) & 31);
-          s[t] = fmaf(-l, s[tp], s[t]);
+      for (int tp = 7; tp >= 1; tp--) {
+        const float4 la = *reinterpret_cast<const float4*>(Lb + tp * 8);
+        float l[8] = {la.x, la.y, la.z, la.w, 0.f, 0.f, 0.f, 0.f};
+        if (tp > 4) {
+          const float4 lb = *reinterpret_cast<const float4*>(Lb + tp * 8 + 4);
+          l[4] = lb.x; l[5] = lb.y; l[6] = lb.z; l[7] = lb.w;
         }
-      }
 #pragma unroll
-      for (int t = 0; t < 8; t++)
-        if (lane == ((jb + t) & 31)) { if (in0) x0 = s[t]; else x1 = s[t]; }
-    }
-    return __all_sync(FULL, isfinite(x0) && isfinite(x1));
+        for (int t = 0; t < tp; t++) s[t] = fmaf(-l[t], s[tp], s[t]);
+      }
+      const float sa = k1 ? s[1] : s[0], sb = k1 ? s[3] : s[2], sc = k1 ? s[5] : s[4], sd = k1 ? s[7] : s[6];
+      const float se = k2 ? sb : sa, sf = k2 ? sd : sc;
+      const float xs = k4 ? sf : se;  // s[lane & 7]
+      if (mine) { if (in0) x0 = xs; else x1 = xs; }
+    });
+    return __all_sync(FULL, good && isfinite(x0) && isfinite(x1));
   }
 };
 

@@ -54,7 +54,7 @@ constexpr int kTmemCols = 512;
 // 640 threads x 96 registers at launch; the register file is per SM sub-partition (16384
 // registers, warp w lives on sub-partition w % 4), so each sub-partition hosts 1 drain, 2
 // Cholesky and 2 producer/MMA warps and setmaxnreg re-balances within 5 x 96 x 32 = 15360:
-constexpr int kRegsProd = 88, kRegsDrain = 48, kRegsChol = 128;
+constexpr int kRegsProd = 80, kRegsDrain = 64, kRegsChol = 128;
 static_assert(32 * (2 * kRegsProd + kRegsDrain + 2 * kRegsChol) <= 5 * 96 * 32, "register pool");
 constexpr bool kCholLockstep = true;   // all Cholesky warps enter each sweep together
 constexpr float kCondLimit = 256.f;  // max diag / min pivot above which a row goes to fp64
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
           uint2 hi, lo;
           split_bf16x2(make_float4(y[ps].x * s, y[ps].y * s, y[ps].z * s, y[ps].w * s), hi, lo);
           const uint32_t oh = offs[ps];
-          const uint32_t ol = (KS == 64) ? oh + 1024u : (oh ^ 64u);
+          const uint32_t ol = (KS == 64) ? (oh ^ 32u) : (oh ^ 64u);
           *reinterpret_cast<uint2*>(stage + oh) = hi;
           *reinterpret_cast<uint2*>(stage + ol) = lo;
           bacc.x = fmaf(cb, y[ps].x, bacc.x);
@@ -333,6 +333,86 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
   } else if (warp < kDrainWarps) {
     // =========================== drain warpgroup =====================================
     reg_dealloc<kRegsDrain>();
+   if constexpr (KS == 64) {
+    // Warp q owns TMEM lane quarter q = matrix rows 16q..16q+15: lanes 0..15 hold the rows'
+    // hi operand halves, lanes 16..31 the lo halves; D's column group g (32 columns) holds
+    // [hi | lo] of features 16g..16g+15 (StageGeom<64>::slots).  Per 16-feature chunk a lane
+    // folds the two column halves, swaps eight values with its partner lane (xor 16) so that
+    // the pair finishes eight columns each, adds G (+ lambda*alpha*n_u on the diagonal) and
+    // stores four float2 of the pair-packed plane.  The four warps never wait for each other.
+    const int qd = warp;
+    const bool upper = lane >= 16;
+    const int i = 16 * qd + (lane & 15);  // matrix row of this lane
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t gseg = 0;
+    int useq = 0;
+    for (long long rb = blockIdx.x; rb < p.n_rows; rb += 32 * row_step) {
+      int cnt_l = 0;
+      {
+        const long long myrow = rb + lane * row_step;
+        if (myrow < p.n_rows) cnt_l = (int)(p.row_ptr[myrow + 1] - p.row_ptr[myrow]);
+      }
+      const long long left = (p.n_rows - rb + row_step - 1) / row_step;
+      const int nb = left < 32 ? (int)left : 32;
+      for (int ib = 0; ib < nb; ib++) {
+        const int cnt = __shfl_sync(kFull, cnt_l, ib);
+        if (cnt == 0) continue;
+        const int nst = (cnt + E - 1) / E;
+        const int nseg = (nst + kSegStages - 1) / kSegStages;
+        const int ws = useq % kWSlots;
+        float* plane = planes + ws * kPlaneF;
+        // W = G + lambda*alpha*n_u*I + ... (ALS.java:447-450, 488-492); padding rows (i >= k)
+        // get a unit diagonal so the factorisation stays finite
+        const float lam_n = (i < k) ? (float)(p.lambda_alpha * (double)cnt) : 1.f;
+        // slot ws last held row useq - kWSlots, consumed by the same Cholesky warp
+        mbar_wait_id(&w_empty[ws], (uint32_t)(((useq / kWSlots) & 1) ^ 1), 4);
+        for (int seg = 0; seg < nseg; seg++, gseg++) {
+          const int a = (int)(gseg % kAccSlots);
+          mbar_wait_id(&acc_full[a], (gseg / kAccSlots) & 1, 5);
+          tc_fence_after_sync();
+          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(a * G::kN);
+          const float* src = (seg == 0) ? g32 : plane;  // later segments add to what this lane stored
+          const float lam = (seg == 0) ? lam_n : 0.f;
+#pragma unroll
+          for (int fc = 0; fc < 4; fc++) {
+            if (fc > qd) break;  // warp-uniform: chunk entirely right of the diagonal
+            uint32_t v0[16], v1[16];
+            tmem_ld_32x16(taddr + 32 * fc, v0);
+            tmem_ld_32x16(taddr + 32 * fc + 16, v1);
+            tmem_wait_ld();
+            float r[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              const float wl = __uint_as_float(v0[e]) + __uint_as_float(v1[e]);          // feature 16fc+e
+              const float wu = __uint_as_float(v0[8 + e]) + __uint_as_float(v1[8 + e]);  // feature 16fc+8+e
+              r[e] = (upper ? wu : wl) + __shfl_xor_sync(kFull, upper ? wl : wu, 16);
+            }
+            // this lane now holds W[i][j0 .. j0+7]
+            const int P0 = 8 * fc + (upper ? 4 : 0);
+#pragma unroll
+            for (int pp = 0; pp < 4; pp++) {
+              const int P = P0 + pp;  // column pair (2P, 2P+1)
+              const int o = 2 * (KS * P - P * (P - 1)) + 2 * (i - 2 * P);
+              if (fc < qd) {          // strictly below the diagonal: no predicates
+                const float2 g = *reinterpret_cast<const float2*>(src + o);
+                *reinterpret_cast<float2*>(plane + o) = make_float2(r[2 * pp] + g.x, r[2 * pp + 1] + g.y);
+              } else if (i >= 2 * P) {
+                const float2 g = *reinterpret_cast<const float2*>(src + o);
+                float2 v = make_float2(r[2 * pp] + g.x, r[2 * pp + 1] + g.y);
+                if (i == 2 * P) { v.x += lam; v.y = 0.f; }
+                else if (i == 2 * P + 1) v.y += lam;
+                *reinterpret_cast<float2*>(plane + o) = v;
+              }
+            }
+          }
+          tc_fence_before_sync();
+          mbar_arrive(&acc_empty[a]);  // accumulator may be overwritten by the next segment
+        }
+        mbar_arrive(&w_full[ws]);  // 128 arrivals: the plane of this row is complete
+        useq++;
+      }
+    }
+   } else {
     const int t = tid;  // 0..127 == TMEM lane
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const bool is_hi = t < KS, is_lo = t >= KS && t < 2 * KS;
@@ -408,6 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
         useq++;
       }
     }
+   }
   } else {
     // =========================== Cholesky warps ======================================
     reg_alloc<kRegsChol>();

@@ -197,8 +197,11 @@ __device__ __forceinline__ void split_bf16x2(const float4 v, uint2& hi, uint2& l
 }
 
 // Geometry of one operand stage for padded feature count KS (32 or 64).
-//   KS=64: one K-step (16 entries) per stage: K-atoms kb=0,1; MN-atoms: 0 = hi, 1 = lo.
-//          atom(kb, mb) at (kb*2 + mb)*1024.  A = B = [hi;lo] : M = N = 128, LBO 1024, SBO 2048.
+//   KS=64: one K-step (16 entries) per stage: K-atoms kb=0,1; two MN-atoms of 64 operand rows.
+//          atom(kb, mb) at (kb*2 + mb)*1024.  A = B : M = N = 128, LBO 1024, SBO 2048.  Operand
+//          row of feature f: hi at (f/16)*32 + f%16, lo at +16 (groups [hi16 | lo16] x 4), so
+//          TMEM lane quarter g / column group g of D hold the hi and lo parts of features
+//          16g..16g+15 side by side.
 //   KS=32: two K-steps (2 x 16 entries) per stage; one MN-atom whose 128-byte row is
 //          [hi(32) | lo(32)]; atom(ks, kb) at ks*2048 + kb*1024.  N = 64, M = 128 (rows
 //          64..127 of D are don't-care), SBO 1024, LBO 1024.
@@ -220,11 +223,14 @@ struct StageGeom {
   __device__ static __forceinline__ void slots(int el, int q, uint32_t& off_hi, uint32_t& off_lo) {
     const int krow = el & 7;
     if (KS == 64) {
+      // M-row of feature f: hi at (f/16)*32 + f%16, lo 16 rows further, so that every TMEM
+      // lane quarter (32 M-rows) holds the hi AND lo halves of the same 16 features
       const int kb = (el >> 3) & 1;
-      const uint32_t row = (uint32_t)(kb * 2) * 1024u + (uint32_t)krow * 128u;
-      const uint32_t in_row = (uint32_t)(((q >> 1) ^ krow) * 16 + (q & 1) * 8);
-      off_hi = row + in_row;
-      off_lo = row + 1024u + in_row;
+      const int g16 = q >> 2, r = q & 3;            // 16-feature group, 4-feature chunk inside it
+      const int chunk = (g16 & 1) * 4 + (r >> 1);   // 16-byte chunk inside the 128-byte atom row
+      const uint32_t row = (uint32_t)(kb * 2 + (g16 >> 1)) * 1024u + (uint32_t)krow * 128u;
+      off_hi = row + (uint32_t)((chunk ^ krow) * 16 + (r & 1) * 8);
+      off_lo = off_hi ^ 32u;                        // chunk + 2
     } else {
       const int ks = (el >> 4) & 1, kb = (el >> 3) & 1;
       const uint32_t row = (uint32_t)ks * 2048u + (uint32_t)kb * 1024u + (uint32_t)krow * 128u;
