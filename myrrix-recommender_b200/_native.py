@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmyrrix_als.so")
+# MYRRIX_ALS_LIB: development override (A/B builds of the same C ABI), never a fallback
+LIB_PATH = os.environ.get("MYRRIX_ALS_LIB") or os.path.join(HERE, "libmyrrix_als.so")
 
 ALS_OK, ALS_E_SINGULAR, ALS_E_NONFINITE, ALS_E_CUDA, ALS_E_NCCL, ALS_E_OOM, ALS_E_ARG, \
     ALS_E_UNSUPPORTED, ALS_E_STATE = range(9)

@@ -6,8 +6,8 @@
 //
 // Forward sweep (right-looking LDL^T, one column per step, KS steps):
 //   every lane publishes its entries of column j (u[i] = W[i][j]) into a double-buffered
-//   KS-float vector in shared memory, the owner of row j adds the pivot d_j and the rhs entry
-//   z_j; one __syncwarp; every lane then reads (d_j, z_j), forms L[i][j] = u[i]/d_j for its own
+//   KS-float vector in shared memory, the pivot d_j and the rhs entry z_j are shuffled out of
+//   the lane that owns row j; one __syncwarp; every lane forms L[i][j] = u[i]/d_j for its own
 //   rows (kept in place of W[i][j]), folds the forward substitution b_i -= L[i][j] z_j, and
 //   updates its rows right of column j with 16-byte broadcast loads of u and packed fp32x2
 //   FMAs:  W[i][c] -= L[i][j] * u[c].  Rows at or above the pivot use a zero multiplier, so
@@ -50,8 +50,12 @@ struct StaticFor {
 };
 
 template <int KS>
-struct CholWarp {
+struct CholWarpRows {
   static_assert(KS == 32 || KS == 64, "in-register Cholesky supports k = 32 or 64");
+  static constexpr int kRowsPerLane = (KS == 64) ? 2 : 1;
+  // matrix row held in slot s of this lane, and whether this lane stores its solution entry
+  __device__ static __forceinline__ int row_of(int lane, int s) { return lane + 32 * s; }
+  __device__ static __forceinline__ bool writes(int, int) { return true; }
   static constexpr bool kTwoRows = (KS == 64);
   // W planes are "pair-packed lower triangles": for column pair P = (2P, 2P+1) the rows
   // i >= 2P are stored as float2 at float offset offP(P) + 2*(i - 2P).  (The .y slot of row
@@ -122,9 +126,23 @@ struct CholWarp {
   // this lane's rows. k: true feature count; padding rows (j >= k) must carry a unit diagonal
   // and are not judged. Returns (warp-uniform) true if the system was solved; x0/x1 then hold
   // the solution entries of rows lane / lane+32.
+  // hook: called once by every lane when the forward sweep reaches column HOOK_STEP (the caller
+  // uses it to hand its input slots back to the upstream roles at a chosen point of the sweep)
+  template <int HOOK_STEP, class Hook>
+  __device__ static __forceinline__ bool factor_solve(Rows& R, float* scratch,
+                                                      float (&bx)[kRowsPerLane], float threshold,
+                                                      float cond_limit, int lane, int k, Hook&& hook) {
+    float x0 = 0.f, x1 = 0.f;
+    const bool ok = factor_solve<HOOK_STEP>(R, scratch, bx[0], kTwoRows ? bx[kRowsPerLane - 1] : 0.f,
+                                            threshold, cond_limit, lane, k, x0, x1, hook);
+    bx[0] = x0;
+    if (kTwoRows) bx[kRowsPerLane - 1] = x1;
+    return ok;
+  }
+  template <int HOOK_STEP, class Hook>
   __device__ static __forceinline__ bool factor_solve(Rows& R, float* scratch, float b0, float b1,
                                                       float threshold, float cond_limit, int lane,
-                                                      int k, float& x0, float& x1) {
+                                                      int k, float& x0, float& x1, Hook&& hook) {
     constexpr unsigned FULL = 0xffffffffu;
     float2 (&A0)[16] = R.A0;
     float2 (&A1)[kP1] = R.A1;
@@ -144,6 +162,7 @@ struct CholWarp {
     // ---- forward sweep ----------------------------------------------------------------------
     StaticFor<0, KS>::run([&](auto jc) {
       constexpr int j = decltype(jc)::value;
+      if constexpr (j == HOOK_STEP) hook();
       float* buf = scratch + (j & 1) * kUBuf;
       constexpr bool piv0 = j < 32;  // the pivot row lives in A0 (else in A1)
       constexpr int own = j & 31;    // lane that owns row j
@@ -151,10 +170,12 @@ struct CholWarp {
       const float w1 = kTwoRows ? get(A1, j) : 0.f;
       if (piv0) buf[lane] = w0;
       if (kTwoRows) buf[32 + lane] = w1;
-      if (lane == own)
-        *reinterpret_cast<float2*>(buf + KS) = piv0 ? make_float2(w0, b0) : make_float2(w1, b1);
+      // pivot d_j and rhs entry z_j straight from their owner lane (shorter dependence chain
+      // than the round trip through shared memory the column itself takes)
+      float2 dz;
+      dz.x = __shfl_sync(FULL, piv0 ? w0 : w1, own);
+      dz.y = __shfl_sync(FULL, piv0 ? b0 : b1, own);
       __syncwarp();
-      const float2 dz = *reinterpret_cast<const float2*>(buf + KS);  // pivot d_j, rhs z_j
       const float inv = fast_rcp(dz.x);
       float m0 = 0.f, m1 = 0.f;  // L[i][j] of my rows; 0 for rows at or above the pivot
       if (piv0) {
@@ -289,5 +310,9 @@ struct CholWarp {
     return __all_sync(FULL, good && isfinite(x0) && isfinite(x1));
   }
 };
+
+
+template <int KS>
+using CholWarp = CholWarpRows<KS>;
 
 }  // namespace als

@@ -37,8 +37,14 @@ __device__ __forceinline__ void report_error(DeviceStatus* st, int code, int whi
 
 // 128-bit read-only gather of factor rows: goes through L1/L2 (rows are re-used
 // across CTAs when the opposite factor fits in the 126 MB L2).
+// (volatile asm: the compiler must issue the load where it is written -- all of a stage's
+// gathers up front -- and not sink it into the conditional block that consumes it)
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
-  return __ldg(reinterpret_cast<const float4*>(p));
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
 }
 // Streaming (read-once) loads for the interaction arrays: do not pollute L1.
 __device__ __forceinline__ int ld_stream_i32(const int* p) {
@@ -50,6 +56,11 @@ __device__ __forceinline__ float ld_stream_f32(const float* p) {
   float v;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
+}
+
+// Ask L2 for the 128-byte line holding p (per-lane, nothing held while it is in flight).
+__device__ __forceinline__ void l2_prefetch_line(const float* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
 }
 
 // Packed fp32x2 FMA (sm_100+): d = a*b + c on two lanes of a 64-bit register pair.

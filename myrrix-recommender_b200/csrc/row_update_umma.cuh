@@ -56,7 +56,14 @@ constexpr int kTmemCols = 512;
 // Cholesky and 2 producer/MMA warps and setmaxnreg re-balances within 5 x 96 x 32 = 15360:
 constexpr int kRegsProd = 80, kRegsDrain = 64, kRegsChol = 128;
 static_assert(32 * (2 * kRegsProd + kRegsDrain + 2 * kRegsChol) <= 5 * 96 * 32, "register pool");
-constexpr bool kCholLockstep = true;   // all Cholesky warps enter each sweep together
+#ifndef ALS_RELEASE_STEP
+#define ALS_RELEASE_STEP 16
+#endif
+constexpr int kReleaseStep = ALS_RELEASE_STEP;  // forward-sweep column at which input slots are released (-1: at once)
+#ifndef ALS_CHOL_LOCKSTEP
+#define ALS_CHOL_LOCKSTEP 1
+#endif
+constexpr bool kCholLockstep = ALS_CHOL_LOCKSTEP != 0;   // all Cholesky warps enter each sweep together
 constexpr float kCondLimit = 256.f;  // max diag / min pivot above which a row goes to fp64
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -285,50 +292,58 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
     }
    } else {
     // =========================== MMA issuer ==========================================
+    // The whole warp runs this loop converged (every value below is warp-uniform, so it lives
+    // in uniform registers); only the tcgen05 instructions themselves are issued by one
+    // elected lane -- always the same one, as tcgen05.commit tracks the MMAs of its own thread.
+    // This loop is the serial resource of the CTA: one trip per 16 entries.
     const uint32_t idesc = make_idesc_bf16_mn(G::kM, G::kN);
-    uint32_t sidx = 0, gseg = 0;
-    for (long long rb = blockIdx.x; rb < p.n_rows; rb += 32 * row_step) {
-      int cnt_l = 0;
-      {
-        const long long myrow = rb + lane * row_step;
-        if (myrow < p.n_rows) cnt_l = (int)(p.row_ptr[myrow + 1] - p.row_ptr[myrow]);
-      }
-      const long long left = (p.n_rows - rb + row_step - 1) / row_step;
-      const int nb = left < 32 ? (int)left : 32;
-      for (int i = 0; i < nb; i++) {
-        const int cnt = __shfl_sync(kFull, cnt_l, i);
-        if (cnt == 0) continue;
-        if (lane == 0) {
-          const int nst = (cnt + E - 1) / E;
-          uint32_t d_tmem = 0;
-          int a = 0;
-          for (int st = 0; st < nst; st++, sidx++) {
-            const bool seg_first = (st % kSegStages) == 0;
-            if (seg_first) {
-              a = (int)(gseg % kAccSlots);
-              mbar_wait_id(&acc_empty[a], ((gseg / kAccSlots) & 1) ^ 1, 2);
-              tc_fence_after_sync();
-              d_tmem = tmem_base + (uint32_t)(a * G::kN);
-            }
-            const int slot = (int)(sidx % kStages);
-            mbar_wait_id(&full[slot], (sidx / kStages) & 1, 3);
-            tc_fence_after_sync();
-            const uint32_t sa = smem_u32(ring + (size_t)slot * G::kBytes);
+    const uint64_t desc0 = make_smem_desc(smem_u32(ring), G::kLBO, G::kSBO);  // slot 0, K-step 0
+    const uint32_t dhi = (uint32_t)(desc0 >> 32);
+    // running ring position: slot, its barriers, the low descriptor word, the phase parity
+    uint32_t slot = 0, par = 0;
+    uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty), dlo = (uint32_t)desc0;
+    uint32_t gseg = 0;
+    // Row lengths come from loads at warp-uniform addresses (not from a per-lane table and
+    // shuffles as in the other roles): only then does the compiler treat the loop as uniform.
+    // The next row's length is fetched one row ahead.
+    long long row = blockIdx.x;
+    int cnt_next = 0;
+#ifdef ALS_MMA_LANE0
+    if (lane == 0)
+#endif
+    {
+    if (row < p.n_rows) cnt_next = (int)(__ldg(p.row_ptr + row + 1) - __ldg(p.row_ptr + row));
+    for (; row < p.n_rows; row += row_step) {
+      const int cnt = cnt_next;
+      const long long nrow = row + row_step;
+      if (nrow < p.n_rows) cnt_next = (int)(__ldg(p.row_ptr + nrow + 1) - __ldg(p.row_ptr + nrow));
+      const int nst = (cnt + E - 1) / E;
+      for (int st0 = 0; st0 < nst; st0 += kSegStages, gseg++) {
+        const int n = (nst - st0 < kSegStages) ? nst - st0 : kSegStages;  // stages of this segment
+        const uint32_t a = gseg % kAccSlots;
+        mbar_wait_id(&acc_empty[a], ((gseg / kAccSlots) & 1) ^ 1, 2);
+        const uint32_t d_tmem = tmem_base + a * (uint32_t)G::kN;
+        for (int t = 0; t < n; t++) {
+          mbar_wait_addr(full_a, par);
+          tc_fence_after_sync();
 #pragma unroll
-            for (int ks = 0; ks < G::kKSteps; ks++) {
-              const uint64_t desc = make_smem_desc(sa + ks * G::kKStepBytes, G::kLBO, G::kSBO);
-              mma_bf16_ss(d_tmem, desc, desc, idesc, (seg_first && ks == 0) ? 0u : 1u);
-            }
-            mma_commit(&empty[slot]);  // frees the operand stage once the MMAs have read it
-            if ((st % kSegStages) == kSegStages - 1 || st == nst - 1) {
-              mma_commit(&acc_full[a]);  // accumulator segment complete
-              gseg++;
-            }
+          for (int ks = 0; ks < G::kKSteps; ks++)
+            mma_bf16_ss_same_elect(d_tmem, dlo + (uint32_t)(ks * (int)(G::kKStepBytes >> 4)), dhi, idesc,
+                                   (t > 0 || ks > 0) ? 1u : 0u);
+          mma_commit_addr_elect(empty_a);  // frees the operand stage once the MMAs have read it
+          slot++; full_a += 8; empty_a += 8; dlo += (uint32_t)(G::kBytes >> 4);
+          if (slot == kStages) {
+            slot = 0; par ^= 1u;
+            full_a -= 8 * kStages; empty_a -= 8 * kStages; dlo -= (uint32_t)(kStages * (G::kBytes >> 4));
           }
         }
-        __syncwarp();
+        mma_commit_elect(&acc_full[a]);  // accumulator segment complete
       }
     }
+    }
+#ifdef ALS_MMA_LANE0
+    __syncwarp();
+#endif
    }
   } else if (warp < kDrainWarps) {
     // =========================== drain warpgroup =====================================
@@ -513,26 +528,53 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
         typename CW::Rows R;
         CW::load(planes + ws * kPlaneF, lane, R);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&w_empty[cw]);  // slot free: the row now lives in registers
+        // The W slot and the rhs slot are handed back to the drain / producers only when the
+        // sweep below reaches column kReleaseStep: the refill they trigger would otherwise
+        // compete with the first, shared-memory-heaviest third of the sweep.
+        if (kReleaseStep < 0 && lane == 0) mbar_arrive(&w_empty[cw]);
         mbar_wait_id(&b_full[cw], (uint32_t)((useq / kBSlots) & 1), 7);
-        float b0 = 0.f, b1 = 0.f;
+        float bx[CW::kRowsPerLane];  // rhs entries of this lane's rows, then the solution
+#pragma unroll
+        for (int s = 0; s < CW::kRowsPerLane; s++) bx[s] = 0.f;
 #pragma unroll
         for (int w = 0; w < kProdWarps; w++) {
-          const float* bp = bpart + (cw * kProdWarps + w) * KS + lane;
-          b0 += bp[0];
-          if (KS == 64) b1 += bp[32];
+          const float* bp = bpart + (cw * kProdWarps + w) * KS;
+#pragma unroll
+          for (int s = 0; s < CW::kRowsPerLane; s++) bx[s] += bp[CW::row_of(lane, s)];
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&b_empty[cw]);
+        if (kReleaseStep < 0 && lane == 0) mbar_arrive(&b_empty[cw]);
         // All Cholesky warps enter the sweep together: they then run the same instruction
         // stream in near lockstep, so the instruction cache sees one stream instead of eight.
-        if (kCholLockstep) bar_sync(1, kCholWarps * 32);
-        float x0, x1;
-        const bool ok = CW::factor_solve(R, scratch, b0, b1, p.threshold, kCondLimit, lane, k, x0, x1);
+        if (kCholLockstep) {
+#ifdef ALS_PROFILE_WAITS
+          const long long tb = clock64();
+          bar_sync(1, kCholWarps * 32);
+          if (lane == 0) atomicAdd(&g_wait_cycles[9], (unsigned long long)(clock64() - tb));
+#else
+          bar_sync(1, kCholWarps * 32);
+#endif
+        }
+#ifdef ALS_PROFILE_WAITS
+        const long long ts = clock64();
+#endif
+        const bool ok = CW::template factor_solve<(kReleaseStep < KS ? kReleaseStep : KS - 1)>(
+            R, scratch, bx, p.threshold, kCondLimit, lane, k, [&]() {
+              if (lane == 0) {
+                mbar_arrive(&w_empty[cw]);
+                mbar_arrive(&b_empty[cw]);
+              }
+            });
+#ifdef ALS_PROFILE_WAITS
+        if (lane == 0) atomicAdd(&g_wait_cycles[10], (unsigned long long)(clock64() - ts));
+#endif
         if (ok) {
           float* dst = p.out + (p.row_offset + row) * KS;
-          if (lane < k) dst[lane] = x0;
-          if (KS == 64 && lane + 32 < k) dst[lane + 32] = x1;
+#pragma unroll
+          for (int s = 0; s < CW::kRowsPerLane; s++) {
+            const int r = CW::row_of(lane, s);
+            if (CW::writes(lane, s) && r < k) dst[r] = bx[s];
+          }
         } else if (lane == 0) {
           const int slot = atomicAdd(p.retry_count, 1);
           p.retry_rows[slot] = (int)row;

@@ -32,7 +32,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
+#ifdef ALS_MBAR_NOHINT
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+#endif
       "selp.b32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
@@ -170,6 +174,81 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
+// Warp-converged variants: every lane executes the call, one elected lane issues (the same
+// lane every time for a full, converged warp).
+__device__ __forceinline__ void mma_bf16_ss_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// A = B = the same operand tile: one descriptor (low word dlo, high word dhi).
+__device__ __forceinline__ void mma_bf16_ss_same_elect(uint32_t tmem_d, uint32_t dlo, uint32_t dhi,
+                                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 d;\n\t"
+      "mov.b64 d, {%1, %2};\n\t"
+#ifdef ALS_MMA_LANE0
+      "setp.eq.b32 q, 0, 0;\n\t"
+#else
+      "elect.sync _|q, 0xffffffff;\n\t"
+#endif
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], d, d, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(dlo), "r"(dhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_addr_elect(uint32_t bar_addr) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+#ifdef ALS_MMA_LANE0
+      "setp.eq.b32 q, 0, 0;\n\t"
+#else
+      "elect.sync _|q, 0xffffffff;\n\t"
+#endif
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(bar_addr)
+      : "memory");
+}
+// spin on an mbarrier given by its shared-window address
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+#ifdef ALS_MBAR_NOHINT
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#else
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+#endif
+      "@!p bra WAIT_%=;\n\t"
+      "}\n" ::"r"(bar_addr), "r"(parity), "r"(1000000u)  // suspend-time hint (ns): sleep, don't spin
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+#ifdef ALS_MMA_LANE0
+      "setp.eq.b32 q, 0, 0;\n\t"
+#else
+      "elect.sync _|q, 0xffffffff;\n\t"
+#endif
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
 // (implicitly performs tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -199,7 +278,8 @@ __device__ __forceinline__ void split_bf16x2(const float4 v, uint2& hi, uint2& l
 // Geometry of one operand stage for padded feature count KS (32 or 64).
 //   KS=64: one K-step (16 entries) per stage: K-atoms kb=0,1; two MN-atoms of 64 operand rows.
 //          atom(kb, mb) at (kb*2 + mb)*1024.  A = B : M = N = 128, LBO 1024, SBO 2048.  Operand
-//          row of feature f: hi at (f/16)*32 + f%16, lo at +16 (groups [hi16 | lo16] x 4), so
+//          row of feature f: hi at (f/16)*32 + f%16, lo at +16 (groups [hi16 | lo16]; the two
+//          groups of the second atom are stored [lo16 | hi16] to spread the stores over banks), so
 //          TMEM lane quarter g / column group g of D hold the hi and lo parts of features
 //          16g..16g+15 side by side.
 //   KS=32: two K-steps (2 x 16 entries) per stage; one MN-atom whose 128-byte row is
@@ -227,10 +307,13 @@ struct StageGeom {
       // lane quarter (32 M-rows) holds the hi AND lo halves of the same 16 features
       const int kb = (el >> 3) & 1;
       const int g16 = q >> 2, r = q & 3;            // 16-feature group, 4-feature chunk inside it
-      const int chunk = (g16 & 1) * 4 + (r >> 1);   // 16-byte chunk inside the 128-byte atom row
+      // 16-byte chunk inside the 128-byte atom row.  The second MN-atom swaps the hi and lo
+      // chunk pairs ([lo16 | hi16] groups): the 16 lanes that store one entry's hi (or lo)
+      // halves then cover all 32 banks, and hi + lo is symmetric for the drain.
+      const int chunk = (g16 & 1) * 4 + (r >> 1) + ((g16 >> 1) ? 2 : 0);
       const uint32_t row = (uint32_t)(kb * 2 + (g16 >> 1)) * 1024u + (uint32_t)krow * 128u;
       off_hi = row + (uint32_t)((chunk ^ krow) * 16 + (r & 1) * 8);
-      off_lo = off_hi ^ 32u;                        // chunk + 2
+      off_lo = off_hi ^ 32u;                        // chunk ^ 2
     } else {
       const int ks = (el >> 4) & 1, kb = (el >> 3) & 1;
       const uint32_t row = (uint32_t)ks * 2048u + (uint32_t)kb * 1024u + (uint32_t)krow * 128u;

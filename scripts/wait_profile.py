@@ -10,7 +10,7 @@ os.makedirs(PROF, exist_ok=True)
 lib = os.path.join(PROF, "libmyrrix_als.so")
 if "--build" in sys.argv:
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-                           "-DALS_PROFILE_WAITS", "-Xcompiler", "-fPIC", "-shared", "-o", lib,
+                           "-DALS_PROFILE_WAITS", *[a for a in sys.argv if a.startswith("-D")], "-Xcompiler", "-fPIC", "-shared", "-o", lib,
                            os.path.join(ROOT, "myrrix-recommender_b200", "csrc", "als_abi.cu"), "-ldl"])
     sys.exit(0)
 import myrrix_recommender_b200 as M
@@ -21,8 +21,8 @@ U, I, nnz, k = cfgs[name]
 L = M._native.load()
 L.als_debug_wait_cycles.argtypes = [C.POINTER(C.c_uint64)]
 names = ["prod:b_empty", "prod:empty", "mma:acc_empty", "mma:full", "drain:w_empty", "drain:acc_full",
-         "chol:w_full", "chol:b_full", "kernel total (per CTA sum)"]
-warps = [7, 7, 1, 1, 4, 4, 8, 8, 1]
+         "chol:w_full", "chol:b_full", "kernel total (per CTA sum)", "chol:lockstep", "chol:factor_solve"]
+warps = [7, 7, 1, 1, 4, 4, 8, 8, 1, 8, 8]
 with M.NativeALS(k) as als:
     als.synth_interactions(U, I, nnz, seed=1234567890)
     als.synth_y0(seed=1234567890)
@@ -34,6 +34,6 @@ with M.NativeALS(k) as als:
         L.als_debug_wait_cycles(buf)
         tot = buf[8] / 148.0
         print("%s-half: kernel cycles per CTA %.3e" % (half, tot))
-        for i in range(8):
+        for i in (0, 1, 2, 3, 4, 5, 6, 7, 9, 10):
             per_warp = buf[i] / 148.0 / warps[i]
             print("   %-16s blocked %5.1f%% of the kernel (avg per warp)" % (names[i], 100.0 * per_warp / tot))
