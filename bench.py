@@ -420,6 +420,8 @@ def main():
             "config": {"workload": WORKLOAD_NAMES[name], "users": U, "items": I,
                        "nnz_per_user": nnz_pu, "features": k, "alpha": 1.0, "lambda": 0.1,
                        "seed": SEED, "kernel": kernel_name,
+                       "warp_roles": ("per launch by row length: 8 solve + 7 gather warps below 384 "
+                                      "entries/row, else 4 + 11") if kernel_name == "tcgen05" else None,
                        "l2": "inputs (>= %.1f GB per half) exceed the 126 MB L2; no flush needed"
                              % (nnz * 8 / 1e9),
                        "parallelism": "1 GPU" if world == 1 else

@@ -324,7 +324,14 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
   if (h->kernel == ALS_KERNEL_TCGEN05) {
     p.retry_rows = h->d_retry_rows;
     p.retry_count = h->d_retry_count;
-    rc = launch_row_update_umma(h->ks, p, h->sm_count, h->stream, h->err, sizeof(h->err));
+    // MYRRIX_ALS_MIX=4|8 forces the warp-role mix (tests, A/B runs); default: by row length
+    int mix_override = 0;
+    if (const char* e = getenv("MYRRIX_ALS_MIX")) {
+      const int v = atoi(e);
+      if (v == 4 || v == 8) mix_override = v;
+    }
+    rc = launch_row_update_umma(h->ks, p, R.nnz, mix_override, h->sm_count, h->stream, h->err,
+                                sizeof(h->err));
     if (rc == ALS_OK) {
       h->launches += 1;
       // fp64 re-solve of the rows the fp32 tensor-core path refused (normally none): the

@@ -38,28 +38,44 @@ namespace als {
 namespace umma {
 
 constexpr int kDrainWarps = 4;                               // warps 0..3   (TMEM lane quarters)
-constexpr int kCholWarps = 8;                                // warps 4..11
-constexpr int kProdWarps = 7;                                // warps 12..18
 constexpr int kFirstChol = kDrainWarps;
-constexpr int kFirstProd = kFirstChol + kCholWarps;
-constexpr int kMmaWarp = kFirstProd + kProdWarps;            // warp 19 (shares the producers' warpgroup)
+constexpr int kMmaWarp = 19;                                 // last warp (shares the producers' warpgroup)
 constexpr int kThreads = (kMmaWarp + 1) * 32;                // 640: 5 warps per SM sub-partition
-constexpr int kStages = 16;                                  // operand ring depth (4 KB each)
 constexpr int kAccSlots = 4;                                 // TMEM accumulators in flight
-constexpr int kWSlots = 8;                                   // W slots (drain -> Cholesky), one per Cholesky warp
-constexpr int kBSlots = 8;                                   // rhs ring depth (== kCholWarps)
-static_assert(kBSlots == kCholWarps && kCholWarps % kWSlots == 0, "ring/consumer phase bookkeeping");
 constexpr int kSegStages = 64;                               // stages per accumulation segment
 constexpr int kTmemCols = 512;
-// 640 threads x 96 registers at launch; the register file is per SM sub-partition (16384
-// registers, warp w lives on sub-partition w % 4), so each sub-partition hosts 1 drain, 2
-// Cholesky and 2 producer/MMA warps and setmaxnreg re-balances within 5 x 96 x 32 = 15360:
-constexpr int kRegsProd = 80, kRegsDrain = 64, kRegsChol = 128;
-static_assert(32 * (2 * kRegsProd + kRegsDrain + 2 * kRegsChol) <= 5 * 96 * 32, "register pool");
-#ifndef ALS_RELEASE_STEP
-#define ALS_RELEASE_STEP 16
+constexpr int kRegsDrain = 64, kRegsChol = 128;
+
+// Role mix of the 15 warps between the drain warpgroup and the MMA issuer: NCHOL Cholesky warps
+// (warps 4 .. 3+NCHOL), the rest producers.  Short rows (the X<-Y half of the headline
+// workload: 100 entries, one k x k solve per 7 stages) are bound by the solves: 8 Cholesky + 7
+// producer warps.  Long rows (the Y<-X half: 1000 entries per solve) are bound by the gather /
+// operand staging: 4 Cholesky + 11 producer warps, a deeper operand ring instead of W slots.
+template <int NCHOL>
+struct Mix {
+  static_assert(NCHOL == 8 || NCHOL == 4, "whole warpgroups per role");
+  static constexpr int kCholWarps = NCHOL;
+  static constexpr int kProdWarps = 15 - NCHOL;
+  static constexpr int kFirstProd = kFirstChol + NCHOL;
+  static constexpr int kStages = (NCHOL == 8) ? 16 : 24;     // operand ring depth (4 KB each)
+  static constexpr int kWSlots = NCHOL;                      // W slots (drain -> Cholesky), one per Cholesky warp
+  static constexpr int kBSlots = NCHOL;                      // rhs ring depth (== kCholWarps)
+  // 640 threads x 96 registers at launch; the register file is per SM sub-partition (16384
+  // registers, warp w lives on sub-partition w % 4): each sub-partition hosts 1 drain warp,
+  // NCHOL/4 Cholesky warps and (16-NCHOL)/4 producer/MMA warps, and setmaxnreg re-balances
+  // within 5 x 96 x 32 = 15360 registers.
+  static constexpr int kRegsProd = (NCHOL == 8) ? 80 : 96;
+  static_assert(32 * (kRegsDrain + (NCHOL / 4) * kRegsChol + ((16 - NCHOL) / 4) * kRegsProd) <= 5 * 96 * 32,
+                "register pool");
+};
+// Forward-sweep column (as a fraction of the sweep: column KS / kReleaseDiv) at which a
+// Cholesky warp hands its W and rhs slots back to the drain / producers; 0 = right after the
+// load.  Measured on the headline X<-Y half (A/B on one box): 1/8 174 ms, 3/16 173, 1/4 168,
+// 5/16 175, 7/16 190, at once 200.
+#ifndef ALS_RELEASE_DIV
+#define ALS_RELEASE_DIV 4
 #endif
-constexpr int kReleaseStep = ALS_RELEASE_STEP;  // forward-sweep column at which input slots are released (-1: at once)
+constexpr int kReleaseDiv = ALS_RELEASE_DIV;
 #ifndef ALS_CHOL_LOCKSTEP
 #define ALS_CHOL_LOCKSTEP 1
 #endif
@@ -67,19 +83,21 @@ constexpr bool kCholLockstep = ALS_CHOL_LOCKSTEP != 0;   // all Cholesky warps e
 constexpr float kCondLimit = 256.f;  // max diag / min pivot above which a row goes to fp64
 constexpr unsigned kFull = 0xffffffffu;
 
-template <int KS>
+template <int KS, int NCHOL>
 struct Smem {
   using CW = CholWarp<KS>;
-  static constexpr size_t kRing = (size_t)kStages * 4096 + 2048;  // +pad: KS=32 A-operand overrun
+  using MX = Mix<NCHOL>;
+  static constexpr size_t kRing = (size_t)MX::kStages * 4096 + 2048;  // +pad: KS=32 A-operand overrun
   static constexpr size_t kPlaneBytes = sizeof(float) * ((CW::kPlane + 3) / 4 * 4);
   static constexpr size_t off_planes = kRing;                                   // [kWSlots]
-  static constexpr size_t off_g32 = off_planes + kWSlots * kPlaneBytes;
+  static constexpr size_t off_g32 = off_planes + MX::kWSlots * kPlaneBytes;
   static constexpr size_t off_bpart = off_g32 + kPlaneBytes;                    // [kBSlots][P][KS]
-  static constexpr size_t off_colbuf = off_bpart + sizeof(float) * kBSlots * kProdWarps * KS;
-  static constexpr size_t off_bars = off_colbuf + sizeof(float) * kCholWarps * CW::kScratch;
-  static constexpr int kNumBars = 2 * kStages + 2 * kAccSlots + 2 * kCholWarps + 2 * kBSlots;
+  static constexpr size_t off_colbuf = off_bpart + sizeof(float) * MX::kBSlots * MX::kProdWarps * KS;
+  static constexpr size_t off_bars = off_colbuf + sizeof(float) * MX::kCholWarps * CW::kScratch;
+  static constexpr int kNumBars = 2 * MX::kStages + 2 * kAccSlots + 2 * MX::kCholWarps + 2 * MX::kBSlots;
   static constexpr size_t off_misc = (off_bars + sizeof(uint64_t) * kNumBars + 15) / 16 * 16;
   static constexpr size_t kTotal = off_misc + 64;
+  static_assert(kTotal <= 227 * 1024, "shared memory per CTA");
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -93,11 +111,16 @@ __device__ __forceinline__ long long shfl_i64(long long v, int src) {
   return ((long long)hi << 32) | (unsigned int)lo;
 }
 
-template <int KS>
+template <int KS, int NCHOL>
 __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowUpdateParams p) {
   using G = StageGeom<KS>;
-  using S = Smem<KS>;
+  using S = Smem<KS, NCHOL>;
   using CW = CholWarp<KS>;
+  using MX = Mix<NCHOL>;
+  constexpr int kCholWarps = MX::kCholWarps, kProdWarps = MX::kProdWarps, kFirstProd = MX::kFirstProd;
+  constexpr int kStages = MX::kStages, kWSlots = MX::kWSlots, kBSlots = MX::kBSlots;
+  constexpr int kRegsProd = MX::kRegsProd;
+  constexpr int kReleaseStep = kReleaseDiv > 0 ? KS / kReleaseDiv : -1;
   // 1024-byte alignment (SWIZZLE_128B atoms) comes from the declaration: no integer
   // round-trip on the pointer, so the compiler keeps every access in the shared window
   // (LDS/STS instead of generic loads); checked once below.
@@ -164,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
   const long long row_step = gridDim.x;
 
   if (warp >= kFirstProd) {
-   reg_dealloc<kRegsProd>();
+   if constexpr (kRegsProd < 96) reg_dealloc<kRegsProd>();
    if (warp < kMmaWarp) {
     // =========================== producers ===========================================
     const int pw = warp - kFirstProd;
@@ -558,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
 #ifdef ALS_PROFILE_WAITS
         const long long ts = clock64();
 #endif
-        const bool ok = CW::template factor_solve<(kReleaseStep < KS ? kReleaseStep : KS - 1)>(
+        const bool ok = CW::template factor_solve<kReleaseStep>(
             R, scratch, bx, p.threshold, kCondLimit, lane, k, [&]() {
               if (lane == 0) {
                 mbar_arrive(&w_empty[cw]);
@@ -599,13 +622,13 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
 
 inline bool umma_supported(int ks) { return ks == 32 || ks == 64; }
 
-template <int KS>
+template <int KS, int NCHOL>
 inline int launch_row_update_umma_t(const RowUpdateParams& p, int sm_count, cudaStream_t stream,
                                     char* err, size_t err_len) {
-  using S = umma::Smem<KS>;
+  using S = umma::Smem<KS, NCHOL>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(umma::row_update_umma_kernel<KS>,
+    cudaError_t e = cudaFuncSetAttribute(umma::row_update_umma_kernel<KS, NCHOL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)S::kTotal);
     if (e != cudaSuccess) {
@@ -616,7 +639,7 @@ inline int launch_row_update_umma_t(const RowUpdateParams& p, int sm_count, cuda
   }
   long long grid = sm_count;
   if (grid > p.n_rows) grid = p.n_rows > 0 ? p.n_rows : 1;
-  umma::row_update_umma_kernel<KS><<<(int)grid, umma::kThreads, S::kTotal, stream>>>(p);
+  umma::row_update_umma_kernel<KS, NCHOL><<<(int)grid, umma::kThreads, S::kTotal, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, err_len, "row_update_umma launch: %s", cudaGetErrorString(e));
@@ -625,11 +648,25 @@ inline int launch_row_update_umma_t(const RowUpdateParams& p, int sm_count, cuda
   return ALS_OK;
 }
 
-inline int launch_row_update_umma(int ks, const RowUpdateParams& p, int sm_count,
-                                  cudaStream_t stream, char* err, size_t err_len) {
+// Average entries per row at which the producer-heavy role mix wins: with 8 Cholesky / 7
+// producer warps a row costs max(solve/8, stages * stage_time/7), with 4 / 11 it costs
+// max(solve/4, stages * stage_time/11); measured solve ~30k cycles, stage_time ~2.5k cycles
+// (16 entries) => crossover near 340 entries per row.
+constexpr long long kLongRowEntries = 384;
+
+// nnz: entries of this launch (all rows).  mix_override: 0 = choose by row length, 4 / 8 = force
+// that many Cholesky warps (tests and A/B runs).
+inline int launch_row_update_umma(int ks, const RowUpdateParams& p, long long nnz, int mix_override,
+                                  int sm_count, cudaStream_t stream, char* err, size_t err_len) {
+  const bool long_rows = mix_override ? (mix_override == 4)
+                                      : (p.n_rows > 0 && nnz / p.n_rows >= kLongRowEntries);
   switch (ks) {
-    case 32: return launch_row_update_umma_t<32>(p, sm_count, stream, err, err_len);
-    case 64: return launch_row_update_umma_t<64>(p, sm_count, stream, err, err_len);
+    case 32:
+      return long_rows ? launch_row_update_umma_t<32, 4>(p, sm_count, stream, err, err_len)
+                       : launch_row_update_umma_t<32, 8>(p, sm_count, stream, err, err_len);
+    case 64:
+      return long_rows ? launch_row_update_umma_t<64, 4>(p, sm_count, stream, err, err_len)
+                       : launch_row_update_umma_t<64, 8>(p, sm_count, stream, err, err_len);
     default:
       snprintf(err, err_len, "tcgen05 kernel supports padded feature counts 32 and 64 only");
       return ALS_E_UNSUPPORTED;

@@ -195,6 +195,35 @@ def test_ragged_rows_one_to_thousands(M, O, kernel):
         assert fro <= TOL and mx <= TOL, (fro, mx)
 
 
+@pytest.mark.parametrize("mix", ["4", "8"])
+@pytest.mark.parametrize("k", [32, 64])
+def test_warp_role_mixes(M, O, monkeypatch, mix, k):
+    """Both role mixes of the tensor-core kernel (8 Cholesky + 7 producer warps for short rows,
+    4 + 11 for long rows; chosen by row length in production, forced here) on the same
+    problem: short user rows, long item rows, a few rows past one accumulation segment."""
+    monkeypatch.setenv("MYRRIX_ALS_MIX", mix)
+    rng = np.random.default_rng(23 + k)
+    n_users, n_items = 1500, 100  # item rows: ~1200 entries (> the 1024-entry segment)
+    lens = np.concatenate([[1, 16, 17, 100], rng.integers(60, 100, size=n_users - 4)])
+    ptr, idx, val = [0], [], []
+    for n in lens:
+        idx += list(np.sort(rng.choice(n_items, size=n, replace=False)))
+        v = rng.integers(1, 6, size=n).astype(np.float32)
+        v[rng.random(n) < 0.05] *= -1
+        val += list(v)
+        ptr.append(len(idx))
+    ptr, idx, val = np.array(ptr, np.int64), np.array(idx, np.int32), np.array(val, np.float32)
+    d = rng.standard_normal((n_items, k))
+    Y0 = (d / np.sqrt((d * d).sum(1))[:, None]).astype(np.float32)
+    Xo, Yo, _, _ = O.als_run(ptr, idx, val, n_items, Y0, max_iterations=3,
+                             convergence_threshold=1e-12, n_threads=8)
+    X, Y, used = _run_gpu(M, ptr, idx, val, n_items, Y0, 3, kernel=2)
+    assert used == 2
+    for a, b in ((X, Xo), (Y, Yo)):
+        fro, mx = rel_err(a, b)
+        assert fro <= TOL and mx <= TOL, (mix, k, fro, mx)
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_singular_reports_rank_like_reference(M, O, kernel):
     """lambda=0 and fewer independent rows than features: the reference throws
