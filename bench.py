@@ -334,8 +334,10 @@ def main():
     dom = "x" if x_ms >= y_ms else "y"
     dom_ms, dom_b = (x_ms, bx) if dom == "x" else (y_ms, by)
     achieved = dom_b / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = None  # measured at N = 1 only (one ncu pass over the full-size launches)
     try:
+        if world > 1:
+            raise LookupError
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             traffic = json.load(f).get("%s_%s_%s" % (name, kernel_name, dom))
     except Exception:
