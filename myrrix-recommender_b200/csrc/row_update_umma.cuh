@@ -2,29 +2,39 @@
 // counts 32 and 64.
 //
 // Same contract as row_update_simt.cuh (Worker.call, AlternatingLeastSquares.java:438-502),
-// different machine mapping.  One persistent CTA (672 threads) per SM, rows strided over
-// CTAs, four warp-specialised roles connected by mbarrier rings:
+// different machine mapping.  One persistent CTA (640 threads, 20 warps) per SM, rows strided
+// over CTAs, four warp-specialised roles connected by mbarrier rings:
 //
-//   producers (8 warps)  each owns every 8th 16/32-entry stage of the CTA's flat stage
-//                        stream: gather the factor rows from HBM (coalesced 16-byte loads),
-//                        scale by sqrt(alpha*|r|), split into bf16 hi + bf16 lo (x ~= hi+lo to
-//                        2^-17, round-to-nearest twice), store both halves into the swizzled
-//                        MN-major operand stage; accumulate the rhs b_u in fp32 on the side.
-//   MMA issuer (1 thread) per 16 entries one tcgen05.mma with A = B = [hi;lo]:
+//   producers (7 or 11)  each owns every 7th/11th 16-entry stage (32 entries at k=32) of the
+//                        CTA's flat stage stream: gather the factor rows from HBM (coalesced
+//                        16-byte loads, all of a stage's gathers issued up front), scale by
+//                        sqrt(alpha*|r|), split into bf16 hi + bf16 lo (x ~= hi+lo to 2^-17,
+//                        round-to-nearest twice), store both halves into the swizzled MN-major
+//                        operand stage; accumulate the rhs b_u in fp32 on the side.
+//   MMA issuer (1 warp)  per 16 entries one tcgen05.mma with A = B = the stage's operand tile:
 //                        D[2k x 2k] += [hi;lo][hi;lo]^T, fp32 accumulate in TMEM (all four
-//                        cross products hi*hi, hi*lo, lo*hi, lo*lo of the rank-16 update).
-//   drain (1 warpgroup)  TMEM -> registers, fold the column halves, add G (fp32 copy in smem)
-//                        and lambda*alpha*n_u, write two pair-packed lower-triangular planes
-//                        (hi rows / lo rows) into a W slot in shared memory.
-//   Cholesky (8 warps)   each takes one row's W slot: in-register fp32 LDL^T + solves
+//                        cross products of the rank-16 update).  The warp runs converged with
+//                        running barrier addresses / descriptor words; one elected lane issues.
+//                        This loop is the CTA's serial resource (one trip per stage).
+//   drain (1 warpgroup)  the operand rows are ordered so that TMEM lane quarter q holds the hi
+//                        and lo halves of matrix rows 16q..16q+15: each drain warp folds columns
+//                        and partner lanes for its own 16 rows, adds G (fp32 copy in smem) and
+//                        lambda*alpha*n_u and writes the pair-packed lower triangle of W_u into a
+//                        W slot in shared memory.  The four warps never wait for each other.
+//   Cholesky (8 or 4)    each takes one row's W slot: in-register fp32 LDL^T + solves
 //                        (chol_warp.cuh), writes the fp32 factor row.  Rows whose pivots look
 //                        singular / ill-conditioned are appended to a retry list and re-solved
 //                        in fp64 by the CUDA-core kernel (which owns the error reporting).
+//                        All Cholesky warps of a CTA enter each sweep together (one instruction
+//                        stream for the 80 KB of straight-line code) and hand their input slots
+//                        back a quarter of the way into the sweep (see kReleaseDiv).
+//
+// The split of the 15 non-drain, non-MMA warps between producers and Cholesky warps is a
+// template parameter chosen per launch from the average row length (Mix<NCHOL> below).
 //
 // Every role walks the CTA's rows in the same order; row lengths are fetched 32 rows at a
-// time (one load per lane, shared by shuffles) so no role ever waits on a dependent
-// row_ptr load per row.  All loops are written for a small instruction footprint: the four
-// roles' hot code must stay resident in the instruction cache together.
+// time (one load per lane, shared by shuffles) so no role waits on a dependent row_ptr load
+// per row (the MMA warp instead loads them one row ahead from warp-uniform addresses).
 //
 // Long rows are cut into segments of kSegStages stages so no fp32 TMEM accumulator carries
 // more than 64 MMA steps before it is folded into the planes.
