@@ -22,7 +22,7 @@ NVCC_FLAGS = [
 
 
 def _sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))  # (csrc_host/ builds separately)
 
 
 def needs_build():
@@ -33,7 +33,24 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in _sources() + [hdr, os.path.abspath(__file__)])
 
 
+INGEST_SRC = os.path.join(HERE, "csrc_host", "ingest.cpp")
+INGEST_LIB = os.path.join(HERE, "libmyrrix_ingest.so")
+CXX = os.environ.get("CXX", "g++")
+
+
+def build_ingest(force=False):
+    """Host-only library (input canonicalisation, include/myrrix_ingest.h): plain g++."""
+    hdr = os.path.join(os.path.dirname(HERE), "include", "myrrix_ingest.h")
+    if (not force and os.path.exists(INGEST_LIB) and
+            all(os.path.getmtime(f) <= os.path.getmtime(INGEST_LIB) for f in (INGEST_SRC, hdr))):
+        return INGEST_LIB
+    subprocess.check_call([CXX, "-O3", "-std=c++17", "-pthread", "-fPIC", "-shared", "-Wall",
+                           "-o", INGEST_LIB, INGEST_SRC])
+    return INGEST_LIB
+
+
 def build(force=False, verbose=False):
+    build_ingest(force)
     if not force and not needs_build():
         return LIB
     cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
