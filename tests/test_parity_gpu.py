@@ -224,6 +224,38 @@ def test_warp_role_mixes(M, O, monkeypatch, mix, k):
         assert fro <= TOL and mx <= TOL, (mix, k, fro, mx)
 
 
+def test_csv_files_to_factors(M, O):
+    """The step in front of the path joined to it: CSV lines with duplicates,
+    deletions, near-zero sums and comments -> libmyrrix_ingest.so -> als_set_interactions ->
+    3 iterations, against the ALS oracle run on the same canonical matrix (the canonicalisation
+    itself is held to its own line-by-line oracle in tests/test_ingest.py)."""
+    from myrrix_recommender_b200 import ingest as ING
+    rng = np.random.default_rng(77)
+    lines = ["user,item,strength"]
+    for _ in range(30000):
+        u, i = int(rng.integers(1000, 1400)), int(rng.integers(-40, 60))
+        r = rng.random()
+        if r < 0.05:
+            lines.append("%d,%d," % (u, i))
+        elif r < 0.15:
+            lines.append("%d,%d" % (u, i))
+        elif r < 0.17:
+            lines.append("# %d" % u)
+        else:
+            lines.append("%d,%d,%.3f" % (u, i, rng.integers(1, 6) * (1 if rng.random() > 0.05 else -1)))
+    res = ING.read_csv_bytes(("\n".join(lines) + "\n").encode())
+    n_users, n_items, k = len(res.user_ids), len(res.item_ids), 16
+    assert n_users > 300 and n_items > 90 and res.col_idx.size > 10000
+    d = rng.standard_normal((n_items, k))
+    Y0 = (d / np.sqrt((d * d).sum(1))[:, None]).astype(np.float32)
+    Xo, Yo, _, _ = O.als_run(res.row_ptr, res.col_idx, res.val, n_items, Y0, max_iterations=3,
+                             convergence_threshold=1e-12, n_threads=8)
+    X, Y, _ = _run_gpu(M, res.row_ptr, res.col_idx, res.val, n_items, Y0, 3)
+    for a, b in ((X, Xo), (Y, Yo)):
+        fro, mx = rel_err(a, b)
+        assert fro <= TOL and mx <= TOL, (fro, mx)
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_singular_reports_rank_like_reference(M, O, kernel):
     """lambda=0 and fewer independent rows than features: the reference throws
