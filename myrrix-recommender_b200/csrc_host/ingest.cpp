@@ -112,6 +112,36 @@ bool parse_long(const char* s, size_t n, int64_t* out) {
 // non-finite, so they are simply refused here.
 bool parse_float(const char* s, size_t n, float* out) {
   if (n == 0 || n > 200) return false;
+  {
+    // Fast path (Clinger): [+-]digits[.digits] with a mantissa below 2^24 and at most 10
+    // fraction digits -- mantissa and power of ten are both exact in fp32, so the single
+    // fp32 division is the correctly rounded result.
+    static const float kPow10[11] = {1e0f, 1e1f, 1e2f, 1e3f, 1e4f, 1e5f, 1e6f, 1e7f, 1e8f, 1e9f, 1e10f};
+    size_t k = 0;
+    const bool neg = s[0] == '-';
+    if (s[0] == '+' || s[0] == '-') k = 1;
+    uint32_t m = 0;
+    int frac = -1, digits = 0;
+    bool simple = k < n;
+    for (; k < n && simple; k++) {
+      const char ch = s[k];
+      if (is_digit(ch)) {
+        m = m * 10 + (uint32_t)(ch - '0');
+        digits++;
+        if (frac >= 0) frac++;
+        if (m >= (1u << 24) || frac > 10) simple = false;
+      } else if (ch == '.' && frac < 0) {
+        frac = 0;
+      } else {
+        simple = false;
+      }
+    }
+    if (simple && digits > 0) {
+      const float v = frac > 0 ? (float)m / kPow10[frac] : (float)m;
+      *out = neg ? -v : v;
+      return true;
+    }
+  }
   size_t i = 0;
   if (s[i] == '+' || s[i] == '-') i++;
   size_t end = n;

@@ -84,6 +84,8 @@ def parse_float(s):
     v = _round_to_f32(exact)
     if not np.isfinite(v):
         raise ValueError(s)
+    if v == 0 and s[0] == "-":
+        v = np.float32(-0.0)  # Float.parseFloat("-0.0") keeps the sign
     return v
 
 

@@ -170,8 +170,15 @@ def test_parse_float_matches_correct_rounding():
     """Float.parseFloat rounds the decimal string to float32 once (no double rounding)."""
     vals = ["0.1", "16777217", "1.00000017881393432617187500001", "3.4028235e38", "1e-45", "7.038531e-26",
             "1.17549435E-38", "0.000099999", "123456.7890123", "4.35", "8.41e21", "2.5e-5d", "0x1.fffffep127"]
+    rng = np.random.default_rng(9)
+    for _ in range(3000):   # short decimals (the single-division fast path) and long ones
+        m = str(int(rng.integers(0, 1 << int(rng.integers(1, 40)))))
+        f = int(rng.integers(0, 13))
+        txt = (m[:-f] or "0") + "." + m[-f:].rjust(f, "0") if f else m
+        vals.append(("-" if rng.random() < 0.3 else "") + txt)
     csv = "\n".join("1,%d,%s" % (k, v) for k, v in enumerate(vals)).encode()
     res = ING.read_csv_bytes(csv, zero_threshold=0.0)
+    assert res.col_idx.size == len(vals)
     for k, v in enumerate(vals):
         assert np.float32(res.val[k]).view(np.uint32) == O.parse_float(v).view(np.uint32), v
 
