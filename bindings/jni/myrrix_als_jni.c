@@ -6,6 +6,7 @@
  * Every function is a 1:1 forward; buffers are direct ByteBuffers so no copy happens here.
  */
 #include <jni.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "myrrix_als.h"
