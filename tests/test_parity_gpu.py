@@ -114,7 +114,8 @@ def test_gramian_golden_and_parity(M, O, goldens):
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("k,n_users,n_items,nnz", [
     (2, 50, 40, 5), (3, 64, 33, 7), (16, 2000, 400, 20), (30, 500, 300, 25),
-    (32, 1500, 500, 50), (64, 1200, 600, 70), (100, 300, 400, 40), (128, 400, 500, 90),
+    (32, 1500, 500, 50), (50, 800, 500, 60), (64, 1200, 600, 70), (100, 300, 400, 40),
+    (128, 400, 500, 90),
 ])
 def test_factor_parity_fixed_iterations(M, O, kernel, k, n_users, n_items, nnz):
     """5 iterations from the same Y0; X and Y within 1e-4 relative of the oracle; 5% negative
