@@ -14,6 +14,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <new>
 #include <string>
 #include <thread>
@@ -183,10 +185,15 @@ bool parse_float(const char* s, size_t n, float* out) {
 }
 
 // ---- long ID -> provisional dense index (order of first appearance) ----------------------------
+// Open addressing, linear probing, key and index in one 16-byte slot (one cache line per probe).
 struct IdMap {
-  std::vector<int64_t> keys;    // slot -> key
-  std::vector<uint32_t> vals;   // slot -> index + 1 (0 = empty)
-  std::vector<int64_t> ids;     // index -> key
+  struct Slot {
+    int64_t key;
+    uint32_t idx1;  // index + 1 (0 = empty)
+    uint32_t pad;
+  };
+  std::vector<Slot> slots;
+  std::vector<int64_t> ids;  // index -> key
   size_t mask = 0;
   IdMap() { rehash(1 << 12); }
   static uint64_t mix(uint64_t x) {
@@ -194,28 +201,27 @@ struct IdMap {
     return x;
   }
   void rehash(size_t cap) {
-    std::vector<int64_t> k(cap);
-    std::vector<uint32_t> v(cap, 0);
+    std::vector<Slot> t(cap, Slot{0, 0, 0});
     mask = cap - 1;
     for (size_t idx = 0; idx < ids.size(); idx++) {
       size_t s = mix((uint64_t)ids[idx]) & mask;
-      while (v[s]) s = (s + 1) & mask;
-      k[s] = ids[idx];
-      v[s] = (uint32_t)idx + 1;
+      while (t[s].idx1) s = (s + 1) & mask;
+      t[s].key = ids[idx];
+      t[s].idx1 = (uint32_t)idx + 1;
     }
-    keys.swap(k);
-    vals.swap(v);
+    slots.swap(t);
   }
+  void prefetch(int64_t key) const { __builtin_prefetch(&slots[mix((uint64_t)key) & mask]); }
   // returns the index, or UINT32_MAX when the 2^31-1 limit is hit
   uint32_t get_or_add(int64_t key) {
     size_t s = mix((uint64_t)key) & mask;
-    while (vals[s]) {
-      if (keys[s] == key) return vals[s] - 1;
+    while (slots[s].idx1) {
+      if (slots[s].key == key) return slots[s].idx1 - 1;
       s = (s + 1) & mask;
     }
     if (ids.size() >= 0x7fffffffu) return 0xffffffffu;
-    keys[s] = key;
-    vals[s] = (uint32_t)ids.size() + 1;
+    slots[s].key = key;
+    slots[s].idx1 = (uint32_t)ids.size() + 1;
     ids.push_back(key);
     if (ids.size() * 10 > (mask + 1) * 7) rehash((mask + 1) * 2);
     return (uint32_t)ids.size() - 1;
@@ -298,7 +304,21 @@ struct Chunk {
   // reference's "more than 100 bad lines and another line arrives" rule across chunks
   std::vector<long long> bad_at;
   bool overflow = false;  // more than 2^31-1 distinct IDs
+  struct Pending { int64_t u, i; float v; };
+  static constexpr int kBatch = 32;
+  Pending pending[kBatch];
+  int n_pending = 0;
 };
+
+void flush_pending(Chunk& c) {
+  for (int k = 0; k < c.n_pending; k++) {
+    const uint32_t u = c.users.get_or_add(c.pending[k].u);
+    const uint32_t i = c.items.get_or_add(c.pending[k].i);
+    if (u == 0xffffffffu || i == 0xffffffffu) { c.overflow = true; continue; }
+    c.events.push_back(LocalEvent{u, i, c.pending[k].v});
+  }
+  c.n_pending = 0;
+}
 
 // One line (no terminator) of chunk c.
 void take_line(Chunk& c, const char* s, size_t n) {
@@ -354,10 +374,12 @@ void take_line(Chunk& c, const char* s, size_t n) {
   if (is_tag[0] && is_tag[1]) return bad(false);       // two tags (:144-148)
   if (is_tag[0]) c.item_tags.push_back(ids[0]);        // itemTagIDs.add(userID)  (:150-152)
   if (is_tag[1]) c.user_tags.push_back(ids[1]);        // userTagIDs.add(itemID)  (:154-156)
-  const uint32_t u = c.users.get_or_add(ids[0]);
-  const uint32_t i = c.items.get_or_add(ids[1]);
-  if (u == 0xffffffffu || i == 0xffffffffu) { c.overflow = true; return; }
-  c.events.push_back(LocalEvent{u, i, value});
+  // the two map probes are cache misses on large inputs: queue the line behind a prefetch of
+  // its slots and resolve a batch at a time (order is preserved)
+  c.users.prefetch(ids[0]);
+  c.items.prefetch(ids[1]);
+  c.pending[c.n_pending++] = Chunk::Pending{ids[0], ids[1], value};
+  if (c.n_pending == Chunk::kBatch) flush_pending(c);
 }
 
 void parse_chunk(Chunk& c) {
@@ -369,6 +391,7 @@ void parse_chunk(Chunk& c) {
     if (e < c.end && *e == '\r' && e + 1 < c.end && e[1] == '\n') e++;  // \r\n
     p = e + 1;
   }
+  flush_pending(c);
 }
 
 }  // namespace
@@ -411,12 +434,19 @@ int ingest_add_file(ingest_handle* h, const char* data, size_t len) {
       chunks[c].end = cut = e;
     }
     chunks[0].starts_input = (h->lines == 0);
+    const bool trace = getenv("MYRRIX_INGEST_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double>(b - a).count();
+    };
+    const auto t0 = now();
     {
       std::vector<std::thread> th;
       for (size_t c = 1; c < parts; c++) th.emplace_back(parse_chunk, std::ref(chunks[c]));
       parse_chunk(chunks[0]);
       for (auto& t : th) t.join();
     }
+    const auto t1 = now();
     // replay "if (badLines > 100) throw" (checked when a line arrives, :95-97) in file order
     for (Chunk& c : chunks) {
       if (c.lines > 0 && h->bad_lines > 100) { h->err = "Too many bad lines; aborting"; return INGEST_E_BAD_LINES; }
@@ -433,12 +463,27 @@ int ingest_add_file(ingest_handle* h, const char* data, size_t len) {
     // sequential reader would have met the IDs in)
     std::vector<std::vector<uint32_t>> umap(parts), imap(parts);
     std::vector<size_t> offset(parts + 1, h->events.size());
+    // (the user and the item map are independent: one thread each; probes run behind a prefetch)
+    auto stitch = [&](bool users) {
+      IdMap& g = users ? h->users : h->items;
+      for (size_t c = 0; c < parts; c++) {
+        const std::vector<int64_t>& ids = users ? chunks[c].users.ids : chunks[c].items.ids;
+        std::vector<uint32_t>& m = users ? umap[c] : imap[c];
+        m.resize(ids.size());
+        constexpr size_t kAhead = 16;
+        for (size_t k = 0; k < ids.size(); k++) {
+          if (k + kAhead < ids.size()) g.prefetch(ids[k + kAhead]);
+          m[k] = g.get_or_add(ids[k]);
+        }
+      }
+    };
+    {
+      std::thread tu(stitch, true);
+      stitch(false);
+      tu.join();
+    }
     for (size_t c = 0; c < parts; c++) {
       Chunk& ch = chunks[c];
-      umap[c].resize(ch.users.ids.size());
-      imap[c].resize(ch.items.ids.size());
-      for (size_t k = 0; k < ch.users.ids.size(); k++) umap[c][k] = h->users.get_or_add(ch.users.ids[k]);
-      for (size_t k = 0; k < ch.items.ids.size(); k++) imap[c][k] = h->items.get_or_add(ch.items.ids[k]);
       for (int64_t t : ch.item_tags) h->item_tags.get_or_add(t);
       for (int64_t t : ch.user_tags) h->user_tags.get_or_add(t);
       offset[c + 1] = offset[c] + ch.events.size();
@@ -447,6 +492,7 @@ int ingest_add_file(ingest_handle* h, const char* data, size_t len) {
       h->err = "more than 2^31-1 distinct users or items";
       return INGEST_E_RANGE;
     }
+    const auto t2 = now();
     h->events.resize(offset[parts]);
     {
       auto emit = [&](size_t c) {
@@ -460,6 +506,9 @@ int ingest_add_file(ingest_handle* h, const char* data, size_t len) {
       emit(0);
       for (auto& t : th) t.join();
     }
+    if (trace)
+      fprintf(stderr, "ingest_add_file: %zu chunks, parse %.3f s, stitch %.3f s, emit %.3f s\n", parts,
+              secs(t0, t1), secs(t1, t2), secs(t2, now()));
   } catch (const std::bad_alloc&) {
     h->err = "out of memory";
     return INGEST_E_OOM;
