@@ -253,34 +253,40 @@ struct ingest_handle {
 
 namespace {
 
-// Stable sort by key on all host threads: equal chunks sorted independently, then merged
-// pairwise (std::inplace_merge keeps the left run first on ties, so input order survives).
-void parallel_stable_sort(std::vector<Event>& ev) {
-  auto by_key = [](const Event& a, const Event& b) { return a.key < b.key; };
-  const size_t n = ev.size();
-  size_t parts = std::thread::hardware_concurrency();
-  if (parts < 1) parts = 1;
-  while (parts > 1 && n / parts < (1u << 16)) parts /= 2;
-  size_t p2 = 1;
-  while (p2 * 2 <= parts) p2 *= 2;  // power of two: a clean merge tree
-  parts = p2;
-  if (parts == 1) { std::stable_sort(ev.begin(), ev.end(), by_key); return; }
-  auto bound = [&](size_t i) { return n / parts * i + std::min(i, n % parts); };
-  {
-    std::vector<std::thread> th;
-    for (size_t i = 0; i < parts; i++)
-      th.emplace_back([&, i] { std::stable_sort(ev.begin() + bound(i), ev.begin() + bound(i + 1), by_key); });
-    for (auto& t : th) t.join();
+// Stable LSD radix sort of one bucket by (user, item).  Only the bits that vary are sorted on:
+// the item index (< n_items) and the user index relative to a lower bound of the bucket's users.
+void radix_sort_events(Event* base, size_t m, uint64_t user_lo, size_t n_items) {
+  if (m < 2) return;
+  if (m < 4096) {
+    std::stable_sort(base, base + m, [](const Event& a, const Event& b) { return a.key < b.key; });
+    return;
   }
-  for (size_t width = 1; width < parts; width *= 2) {
-    std::vector<std::thread> th;
-    for (size_t i = 0; i + width < parts; i += 2 * width)
-      th.emplace_back([&, i, width] {
-        std::inplace_merge(ev.begin() + bound(i), ev.begin() + bound(i + width),
-                           ev.begin() + bound(std::min(i + 2 * width, parts)), by_key);
-      });
-    for (auto& t : th) t.join();
+  int ibits = 1;
+  while (((uint64_t)1 << ibits) < (uint64_t)n_items) ibits++;
+  uint64_t umax = 0;
+  for (size_t e = 0; e < m; e++) umax = std::max(umax, (base[e].key >> 32) - user_lo);
+  int ubits = 1;
+  while (((uint64_t)1 << ubits) <= umax) ubits++;
+  const int total = ibits + ubits;
+  const int passes = (total + 10) / 11;
+  const int digit = (total + passes - 1) / passes;  // <= 11 bits per pass
+  const uint64_t imask = ((uint64_t)1 << ibits) - 1;
+  auto shrink = [&](uint64_t key) { return (((key >> 32) - user_lo) << ibits) | (key & imask); };
+  std::vector<Event> tmp(m);
+  Event* src = base;
+  Event* dst = tmp.data();
+  std::vector<size_t> count((size_t)1 << digit);
+  for (int p = 0; p < passes; p++) {
+    const int shift = p * digit;
+    const uint64_t dmask = ((uint64_t)1 << digit) - 1;
+    std::fill(count.begin(), count.end(), 0);
+    for (size_t e = 0; e < m; e++) count[(shrink(src[e].key) >> shift) & dmask]++;
+    size_t acc = 0;
+    for (size_t d = 0; d < count.size(); d++) { const size_t c = count[d]; count[d] = acc; acc += c; }
+    for (size_t e = 0; e < m; e++) dst[count[(shrink(src[e].key) >> shift) & dmask]++] = src[e];
+    std::swap(src, dst);
   }
+  if (src != base) memcpy(base, src, m * sizeof(Event));
 }
 
 // ---- parsing: a file is cut into chunks at line boundaries and the chunks are parsed on all
@@ -520,52 +526,117 @@ int ingest_finish(ingest_handle* h) {
   if (!h) return INGEST_E_ARG;
   if (h->finished) return INGEST_E_STATE;
   try {
+    // Events are partitioned by user range into one bucket per thread (stable: input order
+    // inside a bucket is kept), and every bucket is sorted by (user, item), folded and turned
+    // into its slice of the CSR independently -- users never straddle buckets.
     std::vector<Event>& ev = h->events;
-    parallel_stable_sort(ev);
-    // fold every cell in input order: increment (fp32 sum) or remove
-    // (FastByIDFloatMap.increment :129-138; MatrixUtils.removeByRow :112-121)
+    const size_t n = ev.size();
     const size_t nu0 = h->users.ids.size(), ni0 = h->items.ids.size();
-    std::vector<uint8_t> user_alive(nu0, 0), item_alive(ni0, 0);
-    size_t w = 0;  // surviving cells are compacted to the front of `ev`
-    for (size_t a = 0; a < ev.size();) {
-      size_t b = a;
-      bool present = false;
-      float sum = 0.f;
-      for (; b < ev.size() && ev[b].key == ev[a].key; b++) {
-        if (isnan(ev[b].v)) present = false;
-        else if (!present) { present = true; sum = ev[b].v; }
-        else sum = sum + ev[b].v;
+    size_t T = h->max_threads > 0 ? (size_t)h->max_threads : std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    while (T > 1 && n < 1024 * T) T--;
+    auto run = [&](auto&& fn) {  // fn(t) for t in [0, T) on T threads
+      std::vector<std::thread> th;
+      for (size_t t = 1; t < T; t++) th.emplace_back(fn, t);
+      fn((size_t)0);
+      for (auto& x : th) x.join();
+    };
+    auto bucket_of = [&](uint64_t key) { return (size_t)((key >> 32) * T / (nu0 ? nu0 : 1)); };
+    auto slice = [&](size_t t) { return n / T * t + std::min(t, n % T); };
+
+    // 1. stable partition by bucket
+    std::vector<size_t> bstart(T + 1, 0);
+    if (T > 1) {
+      std::vector<std::vector<size_t>> cnt(T, std::vector<size_t>(T, 0));
+      run([&](size_t t) {
+        for (size_t e = slice(t); e < slice(t + 1); e++) cnt[t][bucket_of(ev[e].key)]++;
+      });
+      std::vector<std::vector<size_t>> pos(T, std::vector<size_t>(T, 0));
+      size_t acc = 0;
+      for (size_t b = 0; b < T; b++) {
+        bstart[b] = acc;
+        for (size_t t = 0; t < T; t++) { pos[t][b] = acc; acc += cnt[t][b]; }
       }
-      if (present) {
-        user_alive[ev[a].key >> 32] = 1;
-        item_alive[ev[a].key & 0xffffffffu] = 1;
-        ev[w++] = Event{ev[a].key, sum};
-      }
-      a = b;
+      bstart[T] = acc;
+      std::vector<Event> tmp(n);
+      run([&](size_t t) {
+        std::vector<size_t> p = pos[t];
+        for (size_t e = slice(t); e < slice(t + 1); e++) tmp[p[bucket_of(ev[e].key)]++] = ev[e];
+      });
+      ev.swap(tmp);
+    } else {
+      bstart[1] = n;
     }
-    ev.resize(w);
-    // final dense indices: order of first appearance among the survivors (rows whose entries
-    // were all deleted left the maps, MatrixUtils.java:116-119)
+
+    // 2. per bucket: sort, fold every cell in input order -- increment (fp32 sum) or remove
+    //    (FastByIDFloatMap.increment :129-138; MatrixUtils.removeByRow :112-121); surviving
+    //    cells are compacted to the front of the bucket
+    std::vector<uint8_t> user_alive(nu0, 0);
+    std::vector<std::vector<uint8_t>> item_alive_t(T, std::vector<uint8_t>(ni0, 0));
+    std::vector<size_t> kept(T, 0), kept_unpruned(T, 0);
+    const float zt = h->zero_threshold;
+    run([&](size_t t) {
+      Event* base = ev.data() + bstart[t];
+      const size_t m = bstart[t + 1] - bstart[t];
+      radix_sort_events(base, m, nu0 ? (uint64_t)t * nu0 / T : 0, ni0);
+      std::vector<uint8_t>& item_alive = item_alive_t[t];
+      size_t w = 0, unpruned = 0;
+      for (size_t a = 0; a < m;) {
+        size_t b = a;
+        bool present = false;
+        float sum = 0.f;
+        for (; b < m && base[b].key == base[a].key; b++) {
+          if (isnan(base[b].v)) present = false;
+          else if (!present) { present = true; sum = base[b].v; }
+          else sum = sum + base[b].v;
+        }
+        if (present) {
+          user_alive[base[a].key >> 32] = 1;  // users are private to the bucket
+          item_alive[base[a].key & 0xffffffffu] = 1;
+          base[w++] = Event{base[a].key, sum};
+          // removeSmall (:198-211): |v| < threshold leaves the matrix, the (possibly empty) row stays
+          if (!(fabsf(sum) < zt)) unpruned++;
+        }
+        a = b;
+      }
+      kept[t] = w;
+      kept_unpruned[t] = unpruned;
+    });
+
+    // 3. final dense indices: order of first appearance among the survivors (rows whose
+    //    entries were all deleted left the maps, MatrixUtils.java:116-119)
     std::vector<uint32_t> umap(nu0, 0), imap(ni0, 0);
     for (size_t u = 0; u < nu0; u++)
       if (user_alive[u]) { umap[u] = (uint32_t)h->user_ids.size(); h->user_ids.push_back(h->users.ids[u]); }
-    for (size_t i = 0; i < ni0; i++)
-      if (item_alive[i]) { imap[i] = (uint32_t)h->item_ids.size(); h->item_ids.push_back(h->items.ids[i]); }
+    for (size_t i = 0; i < ni0; i++) {
+      bool alive = false;
+      for (size_t t = 0; t < T && !alive; t++) alive = item_alive_t[t][i] != 0;
+      if (alive) { imap[i] = (uint32_t)h->item_ids.size(); h->item_ids.push_back(h->items.ids[i]); }
+    }
     const size_t nu = h->user_ids.size();
+
+    // 4. CSR slices per bucket
+    std::vector<size_t> koff(T + 1, 0), coff(T + 1, 0);
+    for (size_t t = 0; t < T; t++) { koff[t + 1] = koff[t] + kept[t]; coff[t + 1] = coff[t] + kept_unpruned[t]; }
     h->row_ptr.assign(nu + 1, 0);
     h->known_ptr.assign(nu + 1, 0);
-    h->known_idx.reserve(w);
-    for (size_t e = 0; e < w; e++) {
-      const uint32_t u = umap[ev[e].key >> 32], i = imap[ev[e].key & 0xffffffffu];
-      h->known_ptr[u + 1]++;
-      h->known_idx.push_back((int32_t)i);
-      // removeSmall (:198-211): |v| < threshold leaves the matrix, the (possibly empty) row stays
-      if (!(fabsf(ev[e].v) < h->zero_threshold)) {
-        h->row_ptr[u + 1]++;
-        h->col_idx.push_back((int32_t)i);
-        h->val.push_back(ev[e].v);
+    h->known_idx.resize(koff[T]);
+    h->col_idx.resize(coff[T]);
+    h->val.resize(coff[T]);
+    run([&](size_t t) {
+      const Event* base = ev.data() + bstart[t];
+      size_t ko = koff[t], co = coff[t];
+      for (size_t e = 0; e < kept[t]; e++) {
+        const uint32_t u = umap[base[e].key >> 32], i = imap[base[e].key & 0xffffffffu];
+        h->known_ptr[u + 1]++;
+        h->known_idx[ko++] = (int32_t)i;
+        if (!(fabsf(base[e].v) < zt)) {
+          h->row_ptr[u + 1]++;
+          h->col_idx[co] = (int32_t)i;
+          h->val[co++] = base[e].v;
+        }
       }
-    }
+    });
     for (size_t u = 0; u < nu; u++) {
       h->row_ptr[u + 1] += h->row_ptr[u];
       h->known_ptr[u + 1] += h->known_ptr[u];
