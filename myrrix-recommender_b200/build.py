@@ -49,8 +49,23 @@ def build_ingest(force=False):
     return INGEST_LIB
 
 
+FOLDIN_SRC = os.path.join(HERE, "csrc_host", "foldin.cpp")
+FOLDIN_LIB = os.path.join(HERE, "libmyrrix_foldin.so")
+
+
+def build_foldin(force=False):
+    """Host-only library (fold-in math, include/myrrix_foldin.h): plain g++."""
+    hdr = os.path.join(os.path.dirname(HERE), "include", "myrrix_foldin.h")
+    if (not force and os.path.exists(FOLDIN_LIB) and
+            all(os.path.getmtime(f) <= os.path.getmtime(FOLDIN_LIB) for f in (FOLDIN_SRC, hdr))):
+        return FOLDIN_LIB
+    subprocess.check_call([CXX, "-O3", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", FOLDIN_LIB, FOLDIN_SRC])
+    return FOLDIN_LIB
+
+
 def build(force=False, verbose=False):
     build_ingest(force)
+    build_foldin(force)
     if not force and not needs_build():
         return LIB
     cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \

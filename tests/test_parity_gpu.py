@@ -393,3 +393,34 @@ def test_sharded_synthesis_matches_slices_of_the_whole(M, O):
             # which depends on the row set: equal to fp32 rounding, not bit for bit
             assert np.allclose(Y[ib:ie], Y_full[ib:ie], rtol=1e-5, atol=1e-6)
             assert np.array_equal(Y[:ib], Y0[:ib]) and np.array_equal(Y[ie:], Y0[ie:])
+
+
+def test_build_then_fold_in(M, O):
+    """The step after the path: a model build on the GPU, X'X and Y'Y from the
+    resident factors (als_gramian), then online writes folded in by libmyrrix_foldin.so --
+    against the fold-in restatement fed with the oracle's Gramians of the same factors."""
+    from myrrix_recommender_b200 import foldin as FI
+    from oracle import foldin_oracle as FO
+    k = 16
+    ptr, idx, val, Y0 = random_problem(600, 200, 12, k, seed=31, neg_fraction=0.05)
+    with M.NativeALS(k) as als:
+        als.set_interactions(ptr.size - 1, 200, ptr, idx, val)
+        als.set_y(Y0)
+        als.iterate(3)
+        als.sync()
+        X, Y = als.get_x(), als.get_y()
+        GX, GY = als.gramian("x"), als.gramian("y")
+    GXo, GYo = O.transpose_times_self(X), O.transpose_times_self(Y)
+    for a, b in ((GX, GXo), (GY, GYo)):
+        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()
+    rng = np.random.default_rng(32)
+    Xo, Yo = X.copy(), Y.copy()
+    with FI.FoldIn(k, GX, GY) as f:
+        for _ in range(100):
+            u, i = int(rng.integers(len(X))), int(rng.integers(len(Y)))
+            v = float(rng.choice([-1.0, 1.0, 2.0, 5.0]))
+            f.update_features(X[u], Y[i], v)
+            Xo[u], Yo[i] = FO.update_features(Xo[u], Yo[i], v, GXo, GYo)
+    for a, b in ((X, Xo), (Y, Yo)):
+        fro, mx = rel_err(a, b)
+        assert fro <= TOL and mx <= TOL, (fro, mx)
