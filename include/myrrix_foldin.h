@@ -51,6 +51,11 @@ double foldin_weight(const foldin_handle* h, double estimate, float value);
 int foldin_solve(const foldin_handle* h, int32_t which, const float* b, double* x);
 /* updateFeatures: both rows are updated in place from their values on entry. */
 int foldin_update_features(const foldin_handle* h, float* user_features, float* item_features, float value);
+/* n writes applied one after the other (each sees the rows the previous ones left): X [n_users][k]
+ * and Y [n_items][k] row-major, dense row indices; values may be NULL (all 1.0). The reference
+ * does this one setPreference call at a time (ServerRecommender.java:735-760, bulk ingest). */
+int foldin_update_many(const foldin_handle* h, float* X, float* Y, const int32_t* users,
+                       const int32_t* items, const float* values, int64_t n);
 /* buildAnonymousUserFeatures over the n item rows that were found (row-major n x k); values may
  * be NULL (all 1.0). out: k floats. */
 int foldin_anonymous_user(const foldin_handle* h, const float* item_rows, const float* values, int32_t n,

@@ -89,8 +89,9 @@ struct Rrqr {
     }
     return r;
   }
-  void solve(const double* b, double* x) const {
-    std::vector<double> y(b, b + k);
+  // y, z: caller-provided scratch of k doubles each
+  void solve(const double* b, double* x, double* y, double* z) const {
+    memcpy(y, b, sizeof(double) * k);
     for (int minor = 0; minor < k; minor++) {  // y = Q' b
       const double* col = &qrt[(size_t)minor * k];
       double dot = 0;
@@ -98,7 +99,6 @@ struct Rrqr {
       dot /= rdiag[minor] * col[minor];
       for (int r = minor; r < k; r++) y[r] += dot * col[r];
     }
-    std::vector<double> z(k);
     for (int row = k - 1; row >= 0; row--) {  // R z = y
       y[row] /= rdiag[row];
       const double yr = y[row];
@@ -192,9 +192,11 @@ double foldin_weight(const foldin_handle* h, double estimate, float value) {
 int foldin_solve(const foldin_handle* h, int32_t which, const float* b, double* x) {
   if (!h || !b || !x || (which != 0 && which != 1)) return FOLDIN_E_ARG;
   if (!h->have[which]) return FOLDIN_E_NOT_READY;
-  std::vector<double> bd(h->k);
+  thread_local std::vector<double> scratch;  // no allocation per online write
+  if (scratch.size() < 3 * (size_t)h->k) scratch.resize(3 * (size_t)h->k);
+  double* bd = scratch.data();
   for (int i = 0; i < h->k; i++) bd[i] = (double)b[i];
-  h->solver[which].solve(bd.data(), x);
+  h->solver[which].solve(bd, x, bd + h->k, bd + 2 * h->k);
   return FOLDIN_OK;
 }
 
@@ -207,10 +209,13 @@ int foldin_update_features(const foldin_handle* h, float* user, float* item, flo
   if (!isfinite(est)) return FOLDIN_E_NONFINITE;
   const double w = fold_in_weight(h->learn_rate, est, value);
   if (w == 0.0) return FOLDIN_OK;
-  std::vector<double> item_fold(k), user_fold(k);
+  thread_local std::vector<double> folds;
+  if (folds.size() < 2 * (size_t)k) folds.resize(2 * (size_t)k);
+  double* item_fold = folds.data();
+  double* user_fold = folds.data() + k;
   // both solves read the rows as they were on entry (:876-884)
-  if (h->have[0]) foldin_solve(h, 0, user, item_fold.data());
-  if (h->have[1]) foldin_solve(h, 1, item, user_fold.data());
+  if (h->have[0]) foldin_solve(h, 0, user, item_fold);
+  if (h->have[1]) foldin_solve(h, 1, item, user_fold);
   if (h->have[0]) {
     for (int i = 0; i < k; i++) {
       const double delta = w * item_fold[i];
@@ -224,6 +229,17 @@ int foldin_update_features(const foldin_handle* h, float* user, float* item, flo
       if (!isfinite(delta)) return FOLDIN_E_NONFINITE;
       user[i] += (float)delta;
     }
+  }
+  return FOLDIN_OK;
+}
+
+int foldin_update_many(const foldin_handle* h, float* X, float* Y, const int32_t* users,
+                       const int32_t* items, const float* values, int64_t n) {
+  if (!h || !X || !Y || !users || !items || n < 0) return FOLDIN_E_ARG;
+  for (int64_t e = 0; e < n; e++) {
+    const int rc = foldin_update_features(h, X + (size_t)users[e] * h->k, Y + (size_t)items[e] * h->k,
+                                          values ? values[e] : 1.0f);
+    if (rc != FOLDIN_OK) return rc;
   }
   return FOLDIN_OK;
 }

@@ -21,6 +21,7 @@ SYMBOLS = [
     ("foldin_weight", C.c_double, [_H, C.c_double, C.c_float]),
     ("foldin_solve", C.c_int, [_H, C.c_int32, _f32p, _f64p]),
     ("foldin_update_features", C.c_int, [_H, _f32p, _f32p, C.c_float]),
+    ("foldin_update_many", C.c_int, [_H, _f32p, _f32p, _i32p, _i32p, _f32p, C.c_int64]),
     ("foldin_anonymous_user", C.c_int, [_H, _f32p, _f32p, C.c_int32, _f32p]),
 ]
 _lib = None
@@ -101,6 +102,23 @@ class FoldIn:
             raise ArithmeticError("non-finite fold-in")
         if rc != FOLDIN_OK:
             raise RuntimeError("foldin_update_features failed (%d)" % rc)
+
+    def update_many(self, X, Y, users, items, values=None):
+        """A stream of writes applied in order, in place on X [n_users, k] and Y [n_items, k]."""
+        for a in (X, Y):
+            assert a.dtype == np.float32 and a.flags.c_contiguous and a.shape[1] == self.k
+        u = np.ascontiguousarray(users, np.int32)
+        i = np.ascontiguousarray(items, np.int32)
+        assert u.shape == i.shape and (u.size == 0 or (0 <= u.min() and u.max() < len(X) and
+                                                        0 <= i.min() and i.max() < len(Y)))
+        v = None if values is None else np.ascontiguousarray(values, np.float32)
+        rc = self.lib.foldin_update_many(self.h, X.ctypes.data_as(_f32p), Y.ctypes.data_as(_f32p),
+                                         u.ctypes.data_as(_i32p), i.ctypes.data_as(_i32p),
+                                         None if v is None else v.ctypes.data_as(_f32p), u.size)
+        if rc == FOLDIN_E_NONFINITE:
+            raise ArithmeticError("non-finite fold-in")
+        if rc != FOLDIN_OK:
+            raise RuntimeError("foldin_update_many failed (%d)" % rc)
 
     def anonymous_user(self, item_rows, values=None):
         rows = np.ascontiguousarray(item_rows, np.float32).reshape(-1, self.k)

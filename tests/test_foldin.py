@@ -60,6 +60,16 @@ def test_update_features_stream(k):
             Xo[u], Yo[i] = FO.update_features(Xo[u], Yo[i], v, xtx, yty)
     for a, b in ((X, Xo), (Y, Yo)):
         assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()
+    # the same stream through the batched entry point gives the same bits as one call per write
+    rng = np.random.default_rng(100 + k)
+    X2, Y2, _, _ = _model(rng, 400, 250, k)
+    us, its, vs = [], [], []
+    for _ in range(300):
+        us.append(int(rng.integers(len(X2)))); its.append(int(rng.integers(len(Y2))))
+        vs.append(float(rng.choice([-2.0, -1.0, 0.5, 1.0, 3.0])))
+    with FI.FoldIn(k, xtx, yty) as f:
+        f.update_many(X2, Y2, us, its, vs)
+    assert np.array_equal(X2, X) and np.array_equal(Y2, Y)
     assert np.abs(X - _model(np.random.default_rng(100 + k), 400, 250, k)[0]).max() > 1e-4   # it did move
 
 
