@@ -6,9 +6,9 @@ the host-side mirror of the reference interface
  online/src/net/myrrix/online/factorizer/als/AlternatingLeastSquares.java:66) that the
 parity tests and bench.py drive.  No CPU compute path exists here.
 """
-from . import _native, foldin, ingest
+from . import _native, foldin, ingest, model_io
 from .factorizer import (AlternatingLeastSquares, MatrixFactorizer, NativeALS,
                          SingularMatrixSolverException, SolverException, properties)
 
 __all__ = ["AlternatingLeastSquares", "MatrixFactorizer", "NativeALS",
-           "SingularMatrixSolverException", "SolverException", "properties", "_native", "ingest", "foldin"]
+           "SingularMatrixSolverException", "SolverException", "properties", "_native", "ingest", "foldin", "model_io"]

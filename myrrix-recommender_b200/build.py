@@ -63,9 +63,25 @@ def build_foldin(force=False):
     return FOLDIN_LIB
 
 
+MODEL_IO_SRC = os.path.join(HERE, "csrc_host", "model_io.cpp")
+MODEL_IO_LIB = os.path.join(HERE, "libmyrrix_model_io.so")
+
+
+def build_model_io(force=False):
+    """Host-only library (model file codec, include/myrrix_model_io.h): plain g++."""
+    hdr = os.path.join(os.path.dirname(HERE), "include", "myrrix_model_io.h")
+    if (not force and os.path.exists(MODEL_IO_LIB) and
+            all(os.path.getmtime(f) <= os.path.getmtime(MODEL_IO_LIB) for f in (MODEL_IO_SRC, hdr))):
+        return MODEL_IO_LIB
+    subprocess.check_call([CXX, "-O3", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", MODEL_IO_LIB,
+                           MODEL_IO_SRC])
+    return MODEL_IO_LIB
+
+
 def build(force=False, verbose=False):
     build_ingest(force)
     build_foldin(force)
+    build_model_io(force)
     if not force and not needs_build():
         return LIB
     cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \

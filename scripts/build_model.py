@@ -6,7 +6,8 @@ refresh does with the CUDA factorizer plugged in (DelegateGenerationManager.java
 
 Reads every *.csv / *.csv.gz / *.csv.zip of INPUT_DIR (libmyrrix_ingest.so), runs a fixed number
 of ALS iterations (libmyrrix_als.so) from random unit-norm item vectors, and writes
-user_ids, item_ids (int64), X, Y (float32 [n, features]) to an .npz file.
+user_ids, item_ids (int64), X, Y (float32 [n, features]) to an .npz file -- or, when --out ends
+in .gz, the reference's own model.bin.gz (libmyrrix_model_io.so).
 """
 import argparse
 import os
@@ -47,7 +48,13 @@ def main():
         als.sync()
         X, Y = als.get_x(), als.get_y()
     t2 = time.time()
-    np.savez(a.out, user_ids=r.user_ids, item_ids=r.item_ids, X=X, Y=Y)
+    if a.out.endswith(".gz"):   # the reference's model.bin.gz (GenerationSerializer)
+        item_of = r.item_ids
+        g = M.model_io.Generation(r.user_ids, X, r.item_ids, Y, r.user_ids, r.known_ptr,
+                                  item_of[r.known_idx], r.item_tag_ids, r.user_tag_ids)
+        M.model_io.write_generation(g, a.out)
+    else:
+        np.savez(a.out, user_ids=r.user_ids, item_ids=r.item_ids, X=X, Y=Y)
     print("%d iterations in %.2f s -> %s" % (a.iterations, t2 - t1, a.out))
 
 
