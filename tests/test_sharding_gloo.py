@@ -25,7 +25,25 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+def _gramian(M, n, rank, world, sharded):
+    """Full Gramian of the n live rows of replica M; sharded: this rank's block only, summed over
+    ranks with one all-reduce of the k x k fp64 partials (csrc/als_abi.cu: launch_gramian)."""
+    from oracle import oracle as O
+    from myrrix_recommender_b200 import sharding as S
+    if not sharded:
+        return O.transpose_times_self(M[:n])
+    b, e = S.local_block(n, rank, world)
+    k = M.shape[1]
+    part = O.transpose_times_self(M[b:e]) if e > b else np.zeros((k, k))
+    t = torch.from_numpy(np.ascontiguousarray(part))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    G = t.numpy().copy()
+    full = O.transpose_times_self(M[:n])
+    assert np.abs(G - full).max() <= 1e-12 * max(np.abs(full).max(), 1e-300)
+    return G
+
+
+def _worker(rank, world, port, out_dir, sharded_gramian=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -46,7 +64,7 @@ def _worker(rank, world, port, out_dir):
     Y = np.zeros((S.padded_rows(I, world), k), np.float32)
     Y[:I] = Y0
     for _ in range(3):
-        G = O.transpose_times_self(Y[:I])
+        G = _gramian(Y, I, rank, world, sharded_gramian)
         out = X[ub:ue].copy()
         O.als_half(r_ptr, r_idx, r_val, Y[:I], G, out)
         blk = np.zeros((bu, k), np.float32)
@@ -54,7 +72,7 @@ def _worker(rank, world, port, out_dir):
         parts = [torch.zeros(bu, k) for _ in range(world)]
         dist.all_gather(parts, torch.from_numpy(blk))
         X = torch.cat(parts).numpy().copy()
-        G = O.transpose_times_self(X[:U])
+        G = _gramian(X, U, rank, world, sharded_gramian)
         out = Y[ib:ie].copy()
         O.als_half(c_ptr, c_idx, c_val, X[:U], G, out)
         blk = np.zeros((bi, k), np.float32)
@@ -78,6 +96,23 @@ def test_two_rank_sharded_iterations_match_single_process(tmp_path):
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / ("x%d.npy" % r)), Xo)
         assert np.array_equal(np.load(tmp_path / ("y%d.npy" % r)), Yo)
+
+
+def test_two_rank_sharded_gramian_all_reduce(tmp_path):
+    """Each rank reduces the Gramian over its own block, one all-reduce sums the partials: the
+    factors agree with the single-process run (the fp64 sums associate differently, so to
+    rounding of the fp32 results rather than bit for bit) and every rank holds the same bits."""
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), True), nprocs=world, join=True)
+    from conftest import random_problem
+    from oracle import oracle as O
+    ptr, idx, val, Y0 = random_problem(101, 37, 7, 6, seed=21, neg_fraction=0.1, empty_users=2,
+                                       stale_items=1)
+    Xo, Yo, _, _ = O.als_run(ptr, idx, val, 37, Y0, max_iterations=3, convergence_threshold=1e-12)
+    X0, Y0r = np.load(tmp_path / "x0.npy"), np.load(tmp_path / "y0.npy")
+    assert np.array_equal(X0, np.load(tmp_path / "x1.npy")) and np.array_equal(Y0r, np.load(tmp_path / "y1.npy"))
+    assert np.abs(X0 - Xo).max() <= 1e-6 * np.abs(Xo).max()
+    assert np.abs(Y0r - Yo).max() <= 1e-6 * np.abs(Yo).max()
 
 
 def test_block_layout_helpers():
