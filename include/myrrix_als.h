@@ -118,6 +118,16 @@ int als_set_interactions_device(als_handle *h, int64_t n_users, int64_t n_items,
                                 const int64_t *d_row_ptr, const int32_t *d_col_idx,
                                 const float *d_val);
 
+/* Rows that are KEYS of RbyRow (which = 0) / RbyColumn (which = 1) but hold no entries: the
+ * reference reaches them because addWorkers walks every map entry
+ * (AlternatingLeastSquares.java:391-410) and removeSmall empties maps without removing them
+ * (InputFilesReader.java:202-211); it solves W_u = G, b_u = 0, i.e. writes the zero vector (or
+ * throws the singular exception when G is singular).  rows[n]: dense GLOBAL indices, HOST pointer;
+ * every listed row must have no entries.  Call after the interactions are set; a later
+ * als_set_interactions* forgets the lists.  Rows with no entries that are NOT listed stay
+ * "not in the map" (stale rows: carried through untouched, still counted in M^T M). */
+int als_set_present_empty_rows(als_handle *h, int32_t which, const int32_t *rows, int64_t n);
+
 /* setPreviousY (MatrixFactorizer.java:60-64, AlternatingLeastSquares.java:171-174, 304-308):
  * complete initial Y, n_items x features, HOST pointer. Rows of items that have no
  * interactions ("stale" rows) are carried through unchanged and still count in Y^T Y
@@ -143,12 +153,17 @@ int als_probe(als_handle *h, const int32_t *users, int32_t n_users, const int32_
 int als_get_x(als_handle *h, float *out);
 int als_get_y(als_handle *h, float *out);
 
+/* Selected rows of X (which = 0) or Y (which = 1): out[i] = factor[rows[i]], n x features fp32,
+ * HOST pointers (the per-key lookups of getX().get(id) without copying the whole matrix). */
+int als_get_rows(als_handle *h, int32_t which, const int32_t *rows, int32_t n, float *out);
+
 /* M^T M of the current X (which=0) or Y (which=1), features x features fp64, HOST
  * pointer: MatrixUtils.transposeTimesSelf (MatrixUtils.java:219-239). */
 int als_gramian(als_handle *h, int32_t which, double *out);
 
 /* Block until all queued work is done; returns the first deferred error
- * (ALS_E_SINGULAR / ALS_E_NONFINITE / ALS_E_CUDA). */
+ * (ALS_E_SINGULAR / ALS_E_NONFINITE / ALS_E_CUDA).  With a communicator (als_comm_init) the
+ * call is COLLECTIVE: every rank must make it, and every rank gets the first error of any rank. */
 int als_sync(als_handle *h);
 
 /* Message for the last non-OK status on this handle (never NULL). */

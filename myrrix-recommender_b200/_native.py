@@ -52,6 +52,7 @@ SYMBOLS = [
     ("als_set_interactions_by_column", C.c_int, [_H, _i64p, _i32p, _f32p]),
     ("als_set_interactions_device", C.c_int, [_H, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                               C.c_void_p]),
+    ("als_set_present_empty_rows", C.c_int, [_H, C.c_int32, _i32p, C.c_int64]),
     ("als_set_y", C.c_int, [_H, _f32p]),
     ("als_set_x", C.c_int, [_H, _f32p]),
     ("als_half_x", C.c_int, [_H]),
@@ -60,6 +61,7 @@ SYMBOLS = [
     ("als_probe", C.c_int, [_H, _i32p, C.c_int32, _i32p, C.c_int32, _f64p]),
     ("als_get_x", C.c_int, [_H, _f32p]),
     ("als_get_y", C.c_int, [_H, _f32p]),
+    ("als_get_rows", C.c_int, [_H, C.c_int32, _i32p, C.c_int32, _f32p]),
     ("als_gramian", C.c_int, [_H, C.c_int32, _f64p]),
     ("als_sync", C.c_int, [_H]),
     ("als_last_error", C.c_char_p, [_H]),

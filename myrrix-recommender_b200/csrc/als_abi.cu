@@ -18,6 +18,8 @@
 #include "gramian.cuh"
 #include "row_update_simt.cuh"
 #include "row_update_umma.cuh"
+#include "row_update_v2.cuh"
+#include <nvtx3/nvToolsExt.h>
 
 using namespace als;
 
@@ -92,6 +94,20 @@ struct als_handle {
   long long* d_retry_total = nullptr;
   double* d_scratch = nullptr;  // rank kernel scratch + probe output
   int* d_rank = nullptr;
+  // rows that are keys of the reference's map but have no entries (InputFilesReader.removeSmall
+  // leaves the empty maps in place): local row indices per orientation, solved as W = G, b = 0
+  int* d_pe_rows[2] = {nullptr, nullptr};
+  int* d_pe_count[2] = {nullptr, nullptr};
+  long long pe_rows[2] = {0, 0};
+  // per-handle launch configuration (function attributes and occupancy are per device)
+  int simt_blocks_per_sm = 1;
+  int mix_override = 0;   // MYRRIX_ALS_MIX=4|8, read once at als_create
+  bool legacy_umma = false;  // MYRRIX_ALS_V1=1: round-1 tensor-core kernel (A/B runs)
+  // probe scratch (grown on demand, freed with the handle)
+  int* d_probe_idx = nullptr;
+  double* d_probe_out = nullptr;
+  long long probe_idx_cap = 0, probe_out_cap = 0;
+  int* d_flag = nullptr;  // validation / cross-rank status word
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   long long device_bytes = 0;
@@ -279,6 +295,7 @@ int launch_gramian(als_handle* h, const float* M, long long n_rows) {
 int launch_gramian_local(als_handle* h, const float* M, long long n_rows) {
   cudaEvent_t a;
   prof_begin(h, &a);
+  nvtxRangePushA("als:gramian");
   int rc;
   switch (h->ks) {
     case 4: rc = launch_gramian_t<4>(h, M, n_rows); break;
@@ -287,8 +304,9 @@ int launch_gramian_local(als_handle* h, const float* M, long long n_rows) {
     case 32: rc = launch_gramian_t<32>(h, M, n_rows); break;
     case 64: rc = launch_gramian_t<64>(h, M, n_rows); break;
     case 128: rc = launch_gramian_t<128>(h, M, n_rows); break;
-    default: return fail(h, ALS_E_UNSUPPORTED, "padded feature count %d unsupported", h->ks);
+    default: rc = fail(h, ALS_E_UNSUPPORTED, "padded feature count %d unsupported", h->ks); break;
   }
+  nvtxRangePop();
   prof_end(h, a, 0);
   return rc;
 }
@@ -297,21 +315,64 @@ template <int KS>
 int launch_simt_t(als_handle* h, const RowUpdateParams& p) {
   using S = SimtShape<KS>;
   const size_t smem = S::smem_bytes();
-  static bool configured = false;
-  static int blocks_per_sm = 1;
-  if (!configured) {
-    CU(h, cudaFuncSetAttribute(row_update_simt_kernel<KS>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, row_update_simt_kernel<KS>,
-                                                        kSimtThreads, smem));
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-    configured = true;
-  }
-  long long grid = (long long)h->sm_count * blocks_per_sm;
+  long long grid = (long long)h->sm_count * h->simt_blocks_per_sm;
   if (grid > p.n_rows) grid = p.n_rows > 0 ? p.n_rows : 1;
   row_update_simt_kernel<KS><<<(int)grid, kSimtThreads, smem, h->stream>>>(p);
   h->launches += 1;
   CU(h, cudaGetLastError());
+  return ALS_OK;
+}
+
+int launch_simt(als_handle* h, const RowUpdateParams& p) {
+  switch (h->ks) {
+    case 4: return launch_simt_t<4>(h, p);
+    case 8: return launch_simt_t<8>(h, p);
+    case 16: return launch_simt_t<16>(h, p);
+    case 32: return launch_simt_t<32>(h, p);
+    case 64: return launch_simt_t<64>(h, p);
+    case 128: return launch_simt_t<128>(h, p);
+    default: return fail(h, ALS_E_UNSUPPORTED, "padded feature count %d unsupported", h->ks);
+  }
+}
+
+// cudaFuncSetAttribute / occupancy are per device: done once per handle, on the handle's device
+// (als_create), for every kernel instantiation this handle can launch.
+template <int KS>
+int configure_simt_t(als_handle* h) {
+  const size_t smem = SimtShape<KS>::smem_bytes();
+  CU(h, cudaFuncSetAttribute(row_update_simt_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem));
+  int b = 1;
+  CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, row_update_simt_kernel<KS>, kSimtThreads, smem));
+  h->simt_blocks_per_sm = b < 1 ? 1 : b;
+  return ALS_OK;
+}
+template <class K>
+int set_smem_attr(als_handle* h, K kernel, size_t bytes) {
+  CU(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return ALS_OK;
+}
+int configure_kernels(als_handle* h) {
+  int rc;
+  switch (h->ks) {
+    case 4: rc = configure_simt_t<4>(h); break;
+    case 8: rc = configure_simt_t<8>(h); break;
+    case 16: rc = configure_simt_t<16>(h); break;
+    case 32: rc = configure_simt_t<32>(h); break;
+    case 64: rc = configure_simt_t<64>(h); break;
+    case 128: rc = configure_simt_t<128>(h); break;
+    default: return fail(h, ALS_E_UNSUPPORTED, "padded feature count %d unsupported", h->ks);
+  }
+  if (rc != ALS_OK || h->kernel != ALS_KERNEL_TCGEN05) return rc;
+  if (h->ks == 32) {
+    if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<32, 4>, umma::Smem<32, 4>::kTotal)) != ALS_OK) return rc;
+    if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<32, 8>, umma::Smem<32, 8>::kTotal)) != ALS_OK) return rc;
+  } else if (h->ks == 64) {
+    if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<64, 4>, umma::Smem<64, 4>::kTotal)) != ALS_OK) return rc;
+    if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<64, 8>, umma::Smem<64, 8>::kTotal)) != ALS_OK) return rc;
+    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<64, 4>, v2::Smem<64, 4>::kTotal)) != ALS_OK) return rc;
+    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<64, 8>, v2::Smem<64, 8>::kTotal)) != ALS_OK) return rc;
+  }
   return ALS_OK;
 }
 
@@ -336,6 +397,7 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
   p.ticket = h->d_ticket;
   p.row_list = nullptr;
   p.row_list_count = nullptr;
+  p.solve_empty = 0;
   p.retry_rows = nullptr;
   p.retry_count = nullptr;
   CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned long long), h->stream));
@@ -350,44 +412,49 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
   }
   cudaEvent_t a;
   prof_begin(h, &a);
+  nvtxRangePushA(which == 0 ? "als:row_update_x" : "als:row_update_y");
   if (h->kernel == ALS_KERNEL_TCGEN05) {
     p.retry_rows = h->d_retry_rows;
     p.retry_count = h->d_retry_count;
-    // MYRRIX_ALS_MIX=4|8 forces the warp-role mix (tests, A/B runs); default: by row length
-    int mix_override = 0;
-    if (const char* e = getenv("MYRRIX_ALS_MIX")) {
-      const int v = atoi(e);
-      if (v == 4 || v == 8) mix_override = v;
+    // role mix by average row length unless MYRRIX_ALS_MIX forced one at als_create
+    const bool long_rows = h->mix_override ? (h->mix_override == 4)
+                                           : (R.rows > 0 && R.nnz / R.rows >= kLongRowEntries);
+    if (h->ks == 64 && !h->legacy_umma) {
+      rc = long_rows ? launch_row_update_v2_t<64, 4>(p, h->sm_count, h->stream, h->err, sizeof(h->err))
+                     : launch_row_update_v2_t<64, 8>(p, h->sm_count, h->stream, h->err, sizeof(h->err));
+    } else {
+      rc = launch_row_update_umma(h->ks, p, long_rows, h->sm_count, h->stream, h->err, sizeof(h->err));
     }
-    rc = launch_row_update_umma(h->ks, p, R.nnz, mix_override, h->sm_count, h->stream, h->err,
-                                sizeof(h->err));
     if (rc == ALS_OK) {
       h->launches += 1;
       // fp64 re-solve of the rows the fp32 tensor-core path refused (normally none): the
       // CUDA-core kernel in row-list mode; it exits immediately when the list is empty.
       accumulate_count_kernel<<<1, 1, 0, h->stream>>>(h->d_retry_count, h->d_retry_total);
+      h->launches += 1;
       RowUpdateParams q = p;
       q.row_list = h->d_retry_rows;
       q.row_list_count = h->d_retry_count;
       q.retry_rows = nullptr;
       q.retry_count = nullptr;
-      switch (h->ks) {
-        case 32: rc = launch_simt_t<32>(h, q); break;
-        case 64: rc = launch_simt_t<64>(h, q); break;
-        default: rc = ALS_E_UNSUPPORTED; break;
-      }
+      rc = launch_simt(h, q);
     }
   } else {
-    switch (h->ks) {
-      case 4: rc = launch_simt_t<4>(h, p); break;
-      case 8: rc = launch_simt_t<8>(h, p); break;
-      case 16: rc = launch_simt_t<16>(h, p); break;
-      case 32: rc = launch_simt_t<32>(h, p); break;
-      case 64: rc = launch_simt_t<64>(h, p); break;
-      case 128: rc = launch_simt_t<128>(h, p); break;
-      default: rc = fail(h, ALS_E_UNSUPPORTED, "padded feature count %d unsupported", h->ks);
-    }
+    rc = launch_simt(h, p);
   }
+  if (rc == ALS_OK && h->pe_rows[which] > 0) {
+    // present-but-empty rows: W_u = G, b_u = 0 (AlternatingLeastSquares.java:391-410 walks every
+    // map entry; InputFilesReader.java:202-211 leaves emptied maps in place) -> x_u = 0, or
+    // ALS_E_SINGULAR when G itself is singular, through the same fp64 solve as every other row
+    RowUpdateParams q = p;
+    q.row_list = h->d_pe_rows[which];
+    q.row_list_count = h->d_pe_count[which];
+    q.solve_empty = 1;
+    q.retry_rows = nullptr;
+    q.retry_count = nullptr;
+    CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned long long), h->stream));
+    rc = launch_simt(h, q);
+  }
+  nvtxRangePop();
   prof_end(h, a, which == 0 ? 1 : 2);
   return rc;
 }
@@ -499,6 +566,42 @@ int upload_csr(als_handle* h, Csr* c, long long rows, long long row_begin, const
   return ALS_OK;
 }
 
+// Structural check of an uploaded CSR before any kernel dereferences it: row pointers must be
+// non-decreasing and end at nnz, indices must lie in [0, n_cols).  (A bad index would otherwise
+// become an out-of-bounds gather and poison the CUDA context.)
+__global__ void validate_csr_kernel(const long long* __restrict__ ptr, long long rows, long long nnz,
+                                    const int* __restrict__ idx, long long n_cols, int* __restrict__ flag) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool bad = false;
+  for (long long r = t0; r < rows; r += stride) bad |= ptr[r] > ptr[r + 1] || ptr[r] < 0;
+  if (t0 == 0) bad |= ptr[rows] != nnz;
+  for (long long e = t0; e < nnz; e += stride) bad |= idx[e] < 0 || (long long)idx[e] >= n_cols;
+  if (bad) atomicOr(flag, 1);
+}
+int validate_csr(als_handle* h, const Csr& c, long long n_cols, const char* what) {
+  CU(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+  validate_csr_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(c.ptr, c.rows, c.nnz, c.idx, n_cols, h->d_flag);
+  h->launches += 1;
+  int flag = 0;
+  CU(h, cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (flag) return fail(h, ALS_E_ARG, "%s: row pointers not monotone or an index outside [0, %lld)", what, n_cols);
+  return ALS_OK;
+}
+
+// new interactions: forget deferred errors and the present-but-empty lists of the old ones
+int reset_for_new_interactions(als_handle* h) {
+  h->sticky = ALS_OK;
+  h->singular_rank = 0;
+  CU(h, cudaMemsetAsync(h->d_status, 0, sizeof(DeviceStatus), h->stream));
+  for (int w = 0; w < 2; w++) {
+    h->pe_rows[w] = 0;
+    CU(h, cudaMemsetAsync(h->d_pe_count[w], 0, sizeof(int), h->stream));
+  }
+  return ALS_OK;
+}
+
 int check_ready(als_handle* h) {
   if (!h) return ALS_E_ARG;
   if (!h->by_user.ptr || !h->have_by_item || !h->X || !h->Y)
@@ -507,6 +610,37 @@ int check_ready(als_handle* h) {
 }
 
 }  // namespace
+
+template <int KS>
+__global__ void debug_solve_blocked_kernel(const float* __restrict__ W, const float* __restrict__ b, int k,
+                                           float threshold, float* __restrict__ x, int* __restrict__ ok) {
+  using WP = WPanels<KS>;
+  using CB = CholBlocked<KS>;
+  __shared__ __align__(16) float slot[WP::kFloats];
+  __shared__ __align__(16) float scratch[CB::kScratch];
+  const int lane = threadIdx.x;
+  for (int e = lane; e < WP::kFloats; e += 32) slot[e] = 0.f;
+  __syncwarp();
+  for (int e = lane; e < KS * KS; e += 32) {
+    const int i = e / KS, j = e % KS;
+    if (i >= j) {
+      float v = 0.f;
+      if (i < k) v = W[i * k + j];
+      else if (i == j) v = 1.f;  // padding rows: unit diagonal
+      slot[WP::at(i, j)] = -v;
+    }
+  }
+  __syncwarp();
+  float bv[CB::kS];
+#pragma unroll
+  for (int s = 0; s < CB::kS; s++) bv[s] = (lane + 32 * s < k) ? b[lane + 32 * s] : 0.f;
+  const float dmax = CB::diag_max(slot, lane, k);
+  const bool good = CB::factor_solve(slot, scratch, bv, dmax, threshold, v2::kCondLimit, lane, k);
+#pragma unroll
+  for (int s = 0; s < CB::kS; s++)
+    if (lane + 32 * s < k) x[lane + 32 * s] = bv[s];
+  if (lane == 0) *ok = good ? 1 : 0;
+}
 
 // ===========================================================================
 extern "C" {
@@ -563,9 +697,21 @@ int als_create(const als_config* cfg, als_handle** out) {
     return fail(h, ALS_E_UNSUPPORTED, "tcgen05 kernel not available for features=%d", cfg->features);
   h->kernel = (cfg->kernel == ALS_KERNEL_SIMT) ? ALS_KERNEL_SIMT
               : (umma_ok ? ALS_KERNEL_TCGEN05 : ALS_KERNEL_SIMT);
+  // development switches, read once per handle (never on the launch path)
+  if (const char* e = getenv("MYRRIX_ALS_MIX")) {
+    const int v = atoi(e);
+    if (v == 4 || v == 8) h->mix_override = v;
+  }
+  if (const char* e = getenv("MYRRIX_ALS_V1")) h->legacy_umma = atoi(e) != 0;
   CU(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   int rc;
+  if ((rc = configure_kernels(h)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &h->d_flag, 4)) != ALS_OK) return rc;
+  for (int w = 0; w < 2; w++) {
+    if ((rc = dev_alloc(h, &h->d_pe_count[w], 1)) != ALS_OK) return rc;
+    CU(h, cudaMemsetAsync(h->d_pe_count[w], 0, sizeof(int), h->stream));
+  }
   if ((rc = dev_alloc(h, &h->G, (size_t)h->ks * h->ks)) != ALS_OK) return rc;
   if ((rc = dev_alloc(h, &h->d_status, 1)) != ALS_OK) return rc;
   if ((rc = dev_alloc(h, &h->d_ticket, 1)) != ALS_OK) return rc;
@@ -592,6 +738,8 @@ int als_destroy(als_handle* h) {
   cudaFree(h->X); cudaFree(h->Y); cudaFree(h->G); cudaFree(h->G_partial);
   cudaFree(h->d_status); cudaFree(h->d_ticket); cudaFree(h->d_rank); cudaFree(h->d_scratch);
   cudaFree(h->d_retry_rows); cudaFree(h->d_retry_count); cudaFree(h->d_retry_total);
+  cudaFree(h->d_flag); cudaFree(h->d_probe_idx); cudaFree(h->d_probe_out);
+  for (int w = 0; w < 2; w++) { cudaFree(h->d_pe_rows[w]); cudaFree(h->d_pe_count[w]); }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return ALS_OK;
@@ -622,9 +770,14 @@ int als_set_interactions(als_handle* h, int64_t n_users, int64_t n_items, const 
   long long ub, ue;
   local_block(h, h->n_users, &ub, &ue);
   h->have_by_item = false;
+  if ((rc = reset_for_new_interactions(h)) != ALS_OK) return rc;
   rc = upload_csr(h, &h->by_user, ue - ub, ub, (const long long*)row_ptr, col_idx, val,
                   cudaMemcpyHostToDevice);
   if (rc != ALS_OK) return rc;
+  if ((rc = validate_csr(h, h->by_user, h->n_items, "als_set_interactions")) != ALS_OK) {
+    free_csr(h, &h->by_user);
+    return rc;
+  }
   if (h->world == 1) return build_transpose(h);
   CU(h, cudaStreamSynchronize(h->stream));
   return ALS_OK;  // sharded: caller must follow with als_set_interactions_by_column
@@ -640,7 +793,10 @@ int als_set_interactions_by_column(als_handle* h, const int64_t* col_ptr, const 
   int rc = upload_csr(h, &h->by_item, ie - ib, ib, (const long long*)col_ptr, row_idx, val,
                       cudaMemcpyHostToDevice);
   if (rc != ALS_OK) return rc;
-  CU(h, cudaStreamSynchronize(h->stream));
+  if ((rc = validate_csr(h, h->by_item, h->n_users, "als_set_interactions_by_column")) != ALS_OK) {
+    free_csr(h, &h->by_item);
+    return rc;
+  }
   h->have_by_item = true;
   return ALS_OK;
 }
@@ -654,9 +810,14 @@ int als_set_interactions_device(als_handle* h, int64_t n_users, int64_t n_items,
   int rc = set_dims(h, n_users, n_items);
   if (rc != ALS_OK) return rc;
   h->have_by_item = false;
+  if ((rc = reset_for_new_interactions(h)) != ALS_OK) return rc;
   rc = upload_csr(h, &h->by_user, n_users, 0, (const long long*)d_row_ptr, d_col_idx, d_val,
                   cudaMemcpyDeviceToDevice);
   if (rc != ALS_OK) return rc;
+  if ((rc = validate_csr(h, h->by_user, h->n_items, "als_set_interactions_device")) != ALS_OK) {
+    free_csr(h, &h->by_user);
+    return rc;
+  }
   return build_transpose(h);
 }
 
@@ -682,6 +843,29 @@ static int get_factor(als_handle* h, const float* src, long long rows, float* ou
 }
 int als_get_x(als_handle* h, float* out) { return get_factor(h, h ? h->X : nullptr, h ? h->n_users : 0, out); }
 int als_get_y(als_handle* h, float* out) { return get_factor(h, h ? h->Y : nullptr, h ? h->n_items : 0, out); }
+
+int als_get_rows(als_handle* h, int32_t which, const int32_t* rows, int32_t n, float* out) {
+  if (!h || (which != 0 && which != 1) || n < 0 || (n > 0 && (!rows || !out))) return ALS_E_ARG;
+  const float* F = which == 0 ? h->X : h->Y;
+  const long long limit = which == 0 ? h->n_users : h->n_items;
+  if (!F) return fail(h, ALS_E_STATE, "interactions not set");
+  if (n == 0) return ALS_OK;
+  for (int i = 0; i < n; i++)
+    if (rows[i] < 0 || rows[i] >= limit) return fail(h, ALS_E_ARG, "row %d out of range", rows[i]);
+  CU(h, cudaSetDevice(h->device));
+  int* d_rows = nullptr;
+  float* d_out = nullptr;
+  CU(h, cudaMalloc(&d_rows, sizeof(int) * (size_t)n));
+  if (cudaMalloc(&d_out, sizeof(float) * (size_t)n * h->k) != cudaSuccess) { cudaFree(d_rows); return fail(h, ALS_E_OOM, "als_get_rows scratch"); }
+  cudaMemcpyAsync(d_rows, rows, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+  gather_rows_kernel<<<(int)(((long long)n * h->k + 255) / 256), 256, 0, h->stream>>>(F, h->ks, h->k, d_rows, n, d_out);
+  h->launches += 1;
+  cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)n * h->k, cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_rows); cudaFree(d_out);
+  if (e != cudaSuccess) return fail(h, ALS_E_CUDA, "als_get_rows: %s", cudaGetErrorString(e));
+  return ALS_OK;
+}
 
 int als_half_x(als_handle* h) {
   int rc = check_ready(h);
@@ -716,6 +900,37 @@ int als_iterate(als_handle* h, int32_t n_iterations) {
   return ALS_OK;
 }
 
+int als_set_present_empty_rows(als_handle* h, int32_t which, const int32_t* rows, int64_t n) {
+  if (!h || (which != 0 && which != 1) || n < 0 || (n > 0 && !rows)) return ALS_E_ARG;
+  const Csr& c = which == 0 ? h->by_user : h->by_item;
+  if (!c.ptr || (which == 1 && !h->have_by_item)) return fail(h, ALS_E_STATE, "interactions not set");
+  CU(h, cudaSetDevice(h->device));
+  // keep the rows of this rank's block, as local indices; they must have no entries
+  int* local = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  if (!local) return ALS_E_OOM;
+  long long m = 0;
+  const long long n_global = which == 0 ? h->n_users : h->n_items;
+  for (int64_t i = 0; i < n; i++) {
+    const long long r = rows[i];
+    if (r < 0 || r >= n_global) { free(local); return fail(h, ALS_E_ARG, "present-empty row %lld out of range", r); }
+    if (r >= c.row_begin && r < c.row_begin + c.rows) local[m++] = (int)(r - c.row_begin);
+  }
+  dev_free(h, &h->d_pe_rows[which], (size_t)h->pe_rows[which]);
+  h->pe_rows[which] = 0;
+  int rc = ALS_OK;
+  if (m > 0) {
+    if ((rc = dev_alloc(h, &h->d_pe_rows[which], (size_t)m)) != ALS_OK) { free(local); return rc; }
+    cudaMemcpyAsync(h->d_pe_rows[which], local, sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, h->stream);
+  }
+  const int mi = (int)m;
+  cudaMemcpyAsync(h->d_pe_count[which], &mi, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  free(local);
+  if (e != cudaSuccess) return fail(h, ALS_E_CUDA, "present-empty upload: %s", cudaGetErrorString(e));
+  h->pe_rows[which] = m;
+  return ALS_OK;
+}
+
 int als_probe(als_handle* h, const int32_t* users, int32_t n_users, const int32_t* items,
               int32_t n_items, double* out) {
   int rc = check_ready(h);
@@ -729,20 +944,26 @@ int als_probe(als_handle* h, const int32_t* users, int32_t n_users, const int32_
   for (int j = 0; j < n_items; j++)
     if (items[j] < 0 || items[j] >= h->n_items) return fail(h, ALS_E_ARG, "probe item out of range");
   CU(h, cudaSetDevice(h->device));
-  int *d_u = nullptr, *d_i = nullptr;
-  double* d_out = nullptr;
-  CU(h, cudaMalloc(&d_u, sizeof(int) * n_users));
-  CU(h, cudaMalloc(&d_i, sizeof(int) * n_items));
-  CU(h, cudaMalloc(&d_out, sizeof(double) * n));
-  cudaMemcpyAsync(d_u, users, sizeof(int) * n_users, cudaMemcpyHostToDevice, h->stream);
-  cudaMemcpyAsync(d_i, items, sizeof(int) * n_items, cudaMemcpyHostToDevice, h->stream);
+  // scratch lives with the handle: the stop rule probes once per iteration
+  if (h->probe_idx_cap < (long long)n_users + n_items) {
+    dev_free(h, &h->d_probe_idx, (size_t)h->probe_idx_cap);
+    h->probe_idx_cap = (long long)n_users + n_items;
+    if ((rc = dev_alloc(h, &h->d_probe_idx, (size_t)h->probe_idx_cap)) != ALS_OK) { h->probe_idx_cap = 0; return rc; }
+  }
+  if (h->probe_out_cap < n) {
+    dev_free(h, &h->d_probe_out, (size_t)h->probe_out_cap);
+    h->probe_out_cap = n;
+    if ((rc = dev_alloc(h, &h->d_probe_out, (size_t)n)) != ALS_OK) { h->probe_out_cap = 0; return rc; }
+  }
+  int* d_u = h->d_probe_idx;
+  int* d_i = h->d_probe_idx + n_users;
+  CU(h, cudaMemcpyAsync(d_u, users, sizeof(int) * n_users, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(d_i, items, sizeof(int) * n_items, cudaMemcpyHostToDevice, h->stream));
   probe_kernel<<<(int)((n + 127) / 128), 128, 0, h->stream>>>(h->X, h->Y, h->ks, h->k, d_u, n_users,
-                                                             d_i, n_items, d_out);
+                                                             d_i, n_items, h->d_probe_out);
   h->launches += 1;
-  cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
-  cudaError_t e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_u); cudaFree(d_i); cudaFree(d_out);
-  if (e != cudaSuccess) return fail(h, ALS_E_CUDA, "probe: %s", cudaGetErrorString(e));
+  CU(h, cudaMemcpyAsync(out, h->d_probe_out, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
   return ALS_OK;
 }
 
@@ -762,12 +983,26 @@ int als_gramian(als_handle* h, int32_t which, double* out) {
 int als_sync(als_handle* h) {
   if (!h) return ALS_E_ARG;
   CU(h, cudaSetDevice(h->device));
+  // With a communicator als_sync is collective: the first error of ANY rank comes back on every
+  // rank (otherwise the healthy ranks would block in the next half's collectives forever).
+  int global_code = ALS_OK;
+  if (h->comm) {
+    CU(h, cudaMemcpyAsync(h->d_flag + 1, &h->d_status->code, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    ncclResult_t r = g_nccl.AllReduce(h->d_flag + 1, h->d_flag + 2, 1, ncclInt, ncclMax, h->comm, h->stream);
+    if (r != ncclSuccess) return fail(h, ALS_E_NCCL, "ncclAllReduce(status): %s", g_nccl.GetErrorString(r));
+    CU(h, cudaMemcpyAsync(&global_code, h->d_flag + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  }
   CU(h, cudaStreamSynchronize(h->stream));
   prof_drain(h);
   if (h->sticky != ALS_OK) return h->sticky;
   DeviceStatus st;
   CU(h, cudaMemcpy(&st, h->d_status, sizeof(st), cudaMemcpyDeviceToHost));
-  if (st.code == ALS_OK) return ALS_OK;
+  if (st.code == ALS_OK) {
+    if (global_code == ALS_OK) return ALS_OK;
+    h->sticky = global_code;
+    return fail(h, global_code, "another rank reported %s in this half-iteration",
+                global_code == ALS_E_SINGULAR ? "a near-singular row" : "a failure");
+  }
   h->sticky = st.code;
   const char* half = st.which == 0 ? "X" : "Y";
   if (st.code == ALS_E_SINGULAR) {
@@ -854,6 +1089,7 @@ int als_synth_interactions(als_handle* h, int64_t n_users, int64_t n_items, int3
   Csr& A = h->by_user;
   free_csr(h, &A);
   h->have_by_item = false;
+  if ((rc = reset_for_new_interactions(h)) != ALS_OK) return rc;
   A.rows = ue - ub;
   A.nnz = A.rows * nnz_per_user;
   A.row_begin = ub;
@@ -959,6 +1195,37 @@ int als_get_interaction_rows(als_handle* h, int32_t by_column, int64_t first_row
   }
   return ALS_OK;
 }
+
+// ---- development entry points (not part of include/myrrix_als.h) ------------------------------
+// One warp runs the blocked Cholesky (chol_blocked.cuh) on a caller-supplied dense system:
+// checks the solver in isolation from the gather / tensor-core / drain pipeline.
+int als_debug_solve_blocked(const float* W, const float* b, int k, float threshold, float* x, int* ok) {
+  if (!W || !b || !x || !ok || k < 1 || k > 64) return ALS_E_ARG;
+  float *dW = nullptr, *db = nullptr, *dx = nullptr;
+  int* dok = nullptr;
+  cudaMalloc(&dW, sizeof(float) * k * k); cudaMalloc(&db, sizeof(float) * k);
+  cudaMalloc(&dx, sizeof(float) * k); cudaMalloc(&dok, sizeof(int));
+  cudaMemcpy(dW, W, sizeof(float) * k * k, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, b, sizeof(float) * k, cudaMemcpyHostToDevice);
+  if (k <= 32) debug_solve_blocked_kernel<32><<<1, 32>>>(dW, db, k, threshold, dx, dok);
+  else debug_solve_blocked_kernel<64><<<1, 32>>>(dW, db, k, threshold, dx, dok);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaMemcpy(x, dx, sizeof(float) * k, cudaMemcpyDeviceToHost);
+  cudaMemcpy(ok, dok, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(dW); cudaFree(db); cudaFree(dx); cudaFree(dok);
+  return e == cudaSuccess ? ALS_OK : ALS_E_CUDA;
+}
+
+#ifdef ALS_DEBUG_SLOT
+// debug build only (scripts/v2_debug.py): pick the row whose slot the kernel copies out, read it
+int als_debug_set_row(long long row) {
+  return cudaMemcpyToSymbol(als::v2::g_debug_row, &row, sizeof(row)) == cudaSuccess ? 0 : 1;
+}
+int als_debug_get_slot(float* out, int n) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, als::v2::g_debug_slot, sizeof(float) * n) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 #ifdef ALS_PROFILE_WAITS
 // debug build only (scripts/wait_profile.py): read and clear the wait-cycle counters

@@ -73,6 +73,14 @@ __global__ void probe_kernel(const float* __restrict__ X, const float* __restric
   out[t] = dot;
 }
 
+// out[i][0..k) = F[rows[i]][0..k): selected factor rows, unpadded (als_get_rows)
+__global__ void gather_rows_kernel(const float* __restrict__ F, int ks, int k, const int* __restrict__ rows,
+                                   int n, float* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * k) return;
+  out[t] = F[(long long)rows[t / k] * ks + (t % k)];
+}
+
 // ---------------------------------------------------------------------------
 // Synthetic workload. Counter-based: value = f(seed,row,j), so any
 // shard is reproducible without host materialisation. tests/synth_ref.py holds the

@@ -44,6 +44,9 @@ struct RowUpdateParams {
   // Row-list mode (CUDA-core kernel): process only row_list[0 .. *row_list_count).
   const int* row_list;
   const int* row_list_count;
+  // Solve rows without entries too (W_u = G, b_u = 0): set for the list of rows that are keys
+  // of the reference's map but whose entries were all pruned (InputFilesReader.java:202-211).
+  int solve_empty;
   // Filled by the tensor-core kernel: rows it refused (singular / ill-conditioned in fp32).
   int* retry_rows;
   int* retry_count;
@@ -110,7 +113,7 @@ row_update_simt_kernel(const RowUpdateParams p) {
     }
     const long long e0 = p.row_ptr[row], e1 = p.row_ptr[row + 1];
     const long long nu = e1 - e0;
-    if (nu == 0) continue;  // not in the reference's map: leave the factor row untouched
+    if (nu == 0 && !p.solve_empty) continue;  // not in the reference's map: leave the factor row untouched
 
     float2 acc[S::TPT][8];
 #pragma unroll

@@ -635,18 +635,8 @@ inline bool umma_supported(int ks) { return ks == 32 || ks == 64; }
 template <int KS, int NCHOL>
 inline int launch_row_update_umma_t(const RowUpdateParams& p, int sm_count, cudaStream_t stream,
                                     char* err, size_t err_len) {
+  // (the dynamic shared memory opt-in is per device: als_create does it for the handle's device)
   using S = umma::Smem<KS, NCHOL>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(umma::row_update_umma_kernel<KS, NCHOL>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)S::kTotal);
-    if (e != cudaSuccess) {
-      snprintf(err, err_len, "cudaFuncSetAttribute(umma): %s", cudaGetErrorString(e));
-      return ALS_E_CUDA;
-    }
-    configured = true;
-  }
   long long grid = sm_count;
   if (grid > p.n_rows) grid = p.n_rows > 0 ? p.n_rows : 1;
   umma::row_update_umma_kernel<KS, NCHOL><<<(int)grid, umma::kThreads, S::kTotal, stream>>>(p);
@@ -664,12 +654,9 @@ inline int launch_row_update_umma_t(const RowUpdateParams& p, int sm_count, cuda
 // (16 entries) => crossover near 340 entries per row.
 constexpr long long kLongRowEntries = 384;
 
-// nnz: entries of this launch (all rows).  mix_override: 0 = choose by row length, 4 / 8 = force
-// that many Cholesky warps (tests and A/B runs).
-inline int launch_row_update_umma(int ks, const RowUpdateParams& p, long long nnz, int mix_override,
-                                  int sm_count, cudaStream_t stream, char* err, size_t err_len) {
-  const bool long_rows = mix_override ? (mix_override == 4)
-                                      : (p.n_rows > 0 && nnz / p.n_rows >= kLongRowEntries);
+// long_rows: producer-heavy role mix (4 Cholesky + 11 producer warps) instead of 8 + 7.
+inline int launch_row_update_umma(int ks, const RowUpdateParams& p, bool long_rows, int sm_count,
+                                  cudaStream_t stream, char* err, size_t err_len) {
   switch (ks) {
     case 32:
       return long_rows ? launch_row_update_umma_t<32, 4>(p, sm_count, stream, err, err_len)

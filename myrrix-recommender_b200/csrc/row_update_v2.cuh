@@ -1,0 +1,569 @@
+// row_update_v2.cuh -- tensor-core (tcgen05 + TMEM) row update, second generation (k = 64).
+//
+// Same contract as row_update_simt.cuh (Worker.call, AlternatingLeastSquares.java:438-502) and
+// the same four warp-specialised roles and operand layout as row_update_umma.cuh (round 1); what
+// changed is the instruction budget of every role (round-1 profile: 12.3k issued warp
+// instructions per solved row, issue slots and the shared-memory pipe saturated long before
+// HBM):
+//
+//   producers   own every P-th 16-entry stage of the CTA's flat stage stream like before, but
+//               find their stage with one ballot over a per-batch prefix sum of the rows' stage
+//               counts (no per-row cursor walk, no integer modulo), do the per-entry scalar work
+//               (index, sqrt(alpha |r|), rhs weight) once per entry on one lane and hand it to
+//               the 16 lanes of the entry by shuffle, prefetch the next stage's indices / values
+//               while the gathers are in flight, and address the swizzled operand slots as
+//               (lane base) ^ (per-pass constant).  Each producer keeps the partial rhs of ITS
+//               stages of a row in registers and writes it once, when it leaves the row.
+//   MMA issuer  unchanged (one tcgen05.mma per stage, D += [hi;lo][hi;lo]^T); it also signals
+//               "rhs complete" for a row after it has seen the row's last stage.
+//   drain       reads the accumulator with tcgen05.ld.16x256b: the register layout is the
+//               mma.sync accumulator fragment, the hi and lo operand rows of one matrix row
+//               arrive in the SAME thread (two loads, 16 TMEM lanes apart): no shuffles.  Writes
+//               N = -(G + lambda alpha n_u I + D) as 16 x 16 blocks into the panel-major slot.
+//   Cholesky    chol_blocked.cuh: 16-column panels on the CUDA cores, trailing updates as
+//               3xTF32 mma.sync on fragments of the slot, in place.
+#pragma once
+#include "chol_blocked.cuh"
+#include "common.cuh"
+#include "row_update_simt.cuh"  // RowUpdateParams
+#include "umma_common.cuh"
+
+namespace als {
+namespace v2 {
+
+using umma::bar_sync;
+using umma::fence_proxy_async_smem;
+using umma::mbar_arrive;
+using umma::mbar_init;
+using umma::mbar_init_fence;
+using umma::mbar_wait_addr;
+using umma::mbar_wait_id;
+using umma::smem_u32;
+using umma::tc_fence_after_sync;
+using umma::tc_fence_before_sync;
+
+constexpr int kDrainWarps = 4;                 // warps 0..3 (TMEM lane quarters)
+constexpr int kFirstChol = kDrainWarps;
+constexpr int kMmaWarp = 19;
+constexpr int kThreads = (kMmaWarp + 1) * 32;  // 640
+constexpr int kAccSlots = 4;
+constexpr int kSegStages = 64;
+constexpr int kTmemCols = 512;
+constexpr int kRegsDrain = 64;
+#ifndef ALS_V2_REGS_CHOL
+#define ALS_V2_REGS_CHOL 128
+#endif
+constexpr int kRegsChol = ALS_V2_REGS_CHOL;
+constexpr float kCondLimit = 256.f;  // max diag / min pivot above which a row goes to fp64
+constexpr unsigned kFull = 0xffffffffu;
+#ifndef ALS_V2_LOCKSTEP
+#define ALS_V2_LOCKSTEP 1
+#endif
+
+#ifdef ALS_DEBUG_SLOT
+__device__ long long g_debug_row = -1;
+__device__ float g_debug_slot[WPanels<64>::kFloats + 64];
+#endif
+
+template <int NCHOL>
+struct Mix {
+  static_assert(NCHOL == 8 || NCHOL == 4, "whole warpgroups per role");
+  static constexpr int kCholWarps = NCHOL;
+  static constexpr int kProdWarps = 15 - NCHOL;
+  static constexpr int kFirstProd = kFirstChol + NCHOL;
+  static constexpr int kStages = (NCHOL == 8) ? 16 : 24;  // operand ring depth (4 KB each)
+  static constexpr int kRegsProd = (NCHOL == 8) ? 80 : 96;
+  static_assert(32 * (kRegsDrain + (NCHOL / 4) * kRegsChol + ((16 - NCHOL) / 4) * kRegsProd) <= 5 * 96 * 32,
+                "register pool");
+};
+
+template <int KS, int NCHOL>
+struct Smem {
+  using WP = WPanels<KS>;
+  using MX = Mix<NCHOL>;
+  static constexpr size_t kRing = (size_t)MX::kStages * 4096;
+  static constexpr size_t kSlotBytes = sizeof(float) * WP::kFloats;
+  static constexpr size_t off_slots = kRing;                                    // [NCHOL] W slots
+  static constexpr size_t off_ng = off_slots + NCHOL * kSlotBytes;              // -G, panel layout
+  static constexpr size_t off_bpart = off_ng + kSlotBytes;                      // [NCHOL][P][KS]
+  static constexpr size_t off_scratch = off_bpart + sizeof(float) * NCHOL * MX::kProdWarps * KS;
+  static constexpr size_t off_bars = off_scratch + sizeof(float) * NCHOL * CholBlocked<KS>::kScratch;
+  static constexpr int kNumBars = 2 * MX::kStages + 2 * kAccSlots + 4 * NCHOL;
+  static constexpr size_t off_misc = (off_bars + sizeof(uint64_t) * kNumBars + 15) / 16 * 16;
+  static constexpr size_t kTotal = off_misc + 64;
+  static_assert(kTotal <= 227 * 1024, "shared memory per CTA");
+};
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ long long shfl_i64(long long v, int src) {
+  int lo = __shfl_sync(kFull, (int)(v & 0xffffffffLL), src);
+  int hi = __shfl_sync(kFull, (int)(v >> 32), src);
+  return ((long long)hi << 32) | (unsigned int)lo;
+}
+// 16 TMEM lanes x 32 columns of 32-bit in the mma.sync accumulator-fragment layout: for each
+// group i of 8 columns, thread (g = lane/4, t = lane%4) receives v[4i+0..1] = row g, columns
+// 8i+2t, 8i+2t+1 and v[4i+2..3] = row g+8, same columns.  taddr lane field: first of the 16 lanes.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+
+// Row table of a batch of 32 rows (rows rb, rb + step, ...): one row per lane.
+struct RowBatch {
+  long long e0;     // first entry of my row
+  int cnt;          // entries of my row
+  uint32_t end;     // flat index one past my row's last stage (inclusive prefix sum + base)
+  uint32_t ne_mask; // ballot of non-empty rows
+  uint32_t batch_end;
+  int nb;           // rows in this batch
+};
+template <int E>
+__device__ __forceinline__ void load_batch(const RowUpdateParams& p, long long rb, long long row_step,
+                                           int lane, uint32_t base, RowBatch& B) {
+  B.e0 = 0;
+  B.cnt = 0;
+  const long long myrow = rb + lane * row_step;
+  if (myrow < p.n_rows) {
+    B.e0 = p.row_ptr[myrow];
+    B.cnt = (int)(p.row_ptr[myrow + 1] - B.e0);
+  }
+  const long long left = (p.n_rows - rb + row_step - 1) / row_step;
+  B.nb = left < 32 ? (int)left : 32;
+  uint32_t incl = (uint32_t)((B.cnt + E - 1) / E);
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += v;
+  }
+  B.end = base + incl;
+  B.batch_end = __shfl_sync(kFull, B.end, 31);
+  B.ne_mask = __ballot_sync(kFull, B.cnt > 0);
+}
+
+template <int KS, int NCHOL>
+__global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpdateParams p) {
+  static_assert(KS == 64, "second-generation kernel: k = 64");
+  using G = umma::StageGeom<KS>;
+  using S = Smem<KS, NCHOL>;
+  using WP = WPanels<KS>;
+  using CB = CholBlocked<KS>;
+  using MX = Mix<NCHOL>;
+  constexpr int kCholWarps = MX::kCholWarps, P = MX::kProdWarps, kFirstProd = MX::kFirstProd;
+  constexpr int kStages = MX::kStages;
+  constexpr int kRegsProd = MX::kRegsProd;
+  constexpr int E = G::kEntries;  // 16 entries per stage
+  constexpr int kPS = WP::kPS;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* ring = smem;
+  float* slots = reinterpret_cast<float*>(smem + S::off_slots);
+  float* ng = reinterpret_cast<float*>(smem + S::off_ng);
+  float* bpart = reinterpret_cast<float*>(smem + S::off_bpart);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_bars);
+  uint64_t* full = bars;
+  uint64_t* empty = full + kStages;
+  uint64_t* acc_full = empty + kStages;
+  uint64_t* acc_empty = acc_full + kAccSlots;
+  uint64_t* w_full = acc_empty + kAccSlots;
+  uint64_t* w_empty = w_full + kCholWarps;
+  uint64_t* b_full = w_empty + kCholWarps;
+  uint64_t* b_empty = b_full + kCholWarps;
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem + S::off_misc);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int k = p.k;
+  if (tid == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // operand atoms need 1024-byte alignment
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; i++) {
+      mbar_init(&full[i], 32);  // the 32 lanes of the producer warp that owns the stage
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < kAccSlots; i++) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    for (int i = 0; i < kCholWarps; i++) {
+      mbar_init(&w_full[i], 128);
+      mbar_init(&w_empty[i], 1);
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init_fence();
+  }
+  if (warp == kMmaWarp) umma::tmem_alloc(tmem_base_s, kTmemCols);
+  // -G in the panel layout of the slots (padding rows / columns and the unused upper triangles
+  // of the diagonal blocks are 0)
+  for (int e = tid; e < WP::kFloats; e += kThreads) ng[e] = 0.f;
+  __syncthreads();
+  for (int e = tid; e < KS * KS; e += kThreads) {
+    const int i = e / KS, j = e % KS;
+    if (i >= j && i < k) ng[WP::at(i, j)] = -(float)p.G[i * KS + j];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_s;
+  const long long row_step = gridDim.x;
+
+  if (warp >= kFirstProd) {
+   if constexpr (kRegsProd < 96) umma::reg_dealloc<kRegsProd>();
+   if (warp < kMmaWarp) {
+    // =========================== producers ===========================================
+    const int pw = warp - kFirstProd;
+    const int q = lane & 15;    // 16-byte chunk of the factor row / entry slot this lane prepares
+    const int sub = lane >> 4;  // which of the two entries of a pass
+    uint32_t oh0, ol0;
+    G::slots(sub, q, oh0, ol0);  // pass 0; lo = hi ^ 32
+    const uint32_t ring_a = smem_u32(ring);
+    uint32_t f = (uint32_t)pw;       // my next flat stage
+    uint32_t slot = (uint32_t)pw, par = 0;  // its ring slot and phase parity
+    uint32_t base = 0;               // flat index of the first stage of the batch
+    int useq_base = 0;               // non-empty rows before the batch
+    float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float alpha = p.alpha;
+    const bool recon = p.reconstruct_r != 0;
+
+    for (long long rb = blockIdx.x; rb < p.n_rows; rb += 32 * row_step) {
+      RowBatch B;
+      load_batch<E>(p, rb, row_step, lane, base, B);
+      // (row, stage) of flat stage ff inside this batch
+      auto locate = [&](uint32_t ff, int& i, int& st, int& cnt, long long& e0) {
+        i = __ffs(__ballot_sync(kFull, B.end > ff)) - 1;
+        cnt = __shfl_sync(kFull, B.cnt, i);
+        const uint32_t end = __shfl_sync(kFull, B.end, i);
+        st = (int)(ff - (end - (uint32_t)((cnt + E - 1) / E)));
+        e0 = shfl_i64(B.e0, i);
+      };
+      int n_idx = -1;     // prefetched index / value of entry q of my next stage
+      float n_val = 0.f;
+      bool pref = false;
+      while (f < B.batch_end) {
+        int i, st, cnt;
+        long long e0;
+        locate(f, i, st, cnt, e0);
+        const long long es = e0 + (long long)st * E;
+        const int n_here = cnt - st * E;  // >= 1; entries of this stage = min(E, n_here)
+        int my_idx = n_idx;
+        float my_val = n_val;
+        if (!pref) {
+          const bool ok = q < n_here;
+          my_idx = ok ? ld_stream_i32(p.col_idx + es + q) : -1;
+          my_val = ok ? ld_stream_f32(p.val + es + q) : 0.f;
+        }
+        // all gathers of the stage up front
+        float4 y[8];
+#pragma unroll
+        for (int ps = 0; ps < 8; ps++) {
+          const int ci = __shfl_sync(kFull, my_idx, sub + 2 * ps);
+          y[ps] = (ci >= 0) ? ldg_f4(p.M + (long long)ci * KS + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // indices / values of my next stage while the rows are in flight
+        {
+          const uint32_t f2 = f + P;
+          pref = f2 < B.batch_end;
+          if (pref) {
+            int i2, st2, cnt2;
+            long long e02;
+            locate(f2, i2, st2, cnt2, e02);
+            const bool ok = q < cnt2 - st2 * E;
+            const long long es2 = e02 + (long long)st2 * E;
+            n_idx = ok ? ld_stream_i32(p.col_idx + es2 + q) : -1;
+            n_val = ok ? ld_stream_f32(p.val + es2 + q) : 0.f;
+          }
+        }
+        // per-entry scalars, once per entry (lane q of either half):
+        // SYRK weight (c_u - 1) = alpha*|r| (ALS.java:471-479), 0 when reconstructing R (:466-469);
+        // rhs weight r (:466-469) or c_u gated on r > 0 (:480-482)
+        const float ar = alpha * fabsf(my_val);
+        const float my_s = recon ? 0.f : sqrt_approx(ar);
+        const float my_cb = recon ? my_val : (my_val > 0.f ? 1.f + ar : 0.f);
+
+        mbar_wait_id(&empty[slot], par ^ 1u, 1);
+        const uint32_t st_hi = ring_a + slot * (uint32_t)G::kBytes + oh0;  // shared-window address
+#pragma unroll
+        for (int ps = 0; ps < 8; ps++) {
+          const float s = __shfl_sync(kFull, my_s, sub + 2 * ps);
+          const float cb = __shfl_sync(kFull, my_cb, sub + 2 * ps);
+          const float4 v = make_float4(y[ps].x * s, y[ps].y * s, y[ps].z * s, y[ps].w * s);
+          // bf16 hi + bf16 lo, round-to-nearest both times
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y);
+          const __nv_bfloat162 h23 = __floats2bfloat162_rn(v.z, v.w);
+          const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01);
+          const uint32_t u23 = *reinterpret_cast<const uint32_t*>(&h23);
+          const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __uint_as_float(u01 << 16),
+                                                           v.y - __uint_as_float(u01 & 0xffff0000u));
+          const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __uint_as_float(u23 << 16),
+                                                           v.w - __uint_as_float(u23 & 0xffff0000u));
+          // pass ps fills K-row 2(ps&3)+sub of K-atom ps>>2: relative to pass 0 the slot address
+          // differs by ^((ps&3) << 5) (the swizzle), ^((ps&3) << 8) (the K-row; both below the
+          // ring's 1 KB alignment, so XOR on the address is exact) and + (ps>>2) * 2048
+          const uint32_t xo = (uint32_t)(((ps & 3) << 5) | ((ps & 3) << 8));
+          const uint32_t ko = (uint32_t)((ps >> 2) << 11);
+          sts_v2((st_hi ^ xo) + ko, u01, u23);
+          sts_v2((st_hi ^ (xo ^ 32u)) + ko, *reinterpret_cast<const uint32_t*>(&l01),
+                 *reinterpret_cast<const uint32_t*>(&l23));
+          bacc.x = fmaf(cb, y[ps].x, bacc.x);
+          bacc.y = fmaf(cb, y[ps].y, bacc.y);
+          bacc.z = fmaf(cb, y[ps].z, bacc.z);
+          bacc.w = fmaf(cb, y[ps].w, bacc.w);
+        }
+        // my last stage of this row: publish the partial rhs of my stages (before the stage's
+        // `full` arrive: the MMA warp's "rhs complete" signal then covers it)
+        if (st + P >= (cnt + E - 1) / E) {
+          const int useq = useq_base + __popc(B.ne_mask & ((1u << i) - 1u));
+          const int bslot = useq % kCholWarps;
+          float4 v = bacc;
+          v.x += __shfl_xor_sync(kFull, v.x, 16);
+          v.y += __shfl_xor_sync(kFull, v.y, 16);
+          v.z += __shfl_xor_sync(kFull, v.z, 16);
+          v.w += __shfl_xor_sync(kFull, v.w, 16);
+          mbar_wait_id(&b_empty[bslot], (uint32_t)(((useq / kCholWarps) & 1) ^ 1), 0);
+          if (lane < 16) *reinterpret_cast<float4*>(bpart + (bslot * P + pw) * KS + 4 * q) = v;
+          bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&full[slot]);
+        f += P;
+        slot += P;
+        if (slot >= (uint32_t)kStages) { slot -= kStages; par ^= 1u; }
+      }
+      base = B.batch_end;
+      useq_base += __popc(B.ne_mask);
+    }
+   } else {
+    // =========================== MMA issuer ==========================================
+    // The whole warp runs this loop converged; only the tcgen05 instructions are issued by one
+    // elected lane.  One trip per 16 entries: the serial resource of the CTA.
+    const uint32_t idesc = umma::make_idesc_bf16_mn(G::kM, G::kN);
+    const uint64_t desc0 = umma::make_smem_desc(smem_u32(ring), G::kLBO, G::kSBO);
+    const uint32_t dhi = (uint32_t)(desc0 >> 32);
+    uint32_t slot = 0, par = 0;
+    uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty), dlo = (uint32_t)desc0;
+    uint32_t gseg = 0;
+    uint32_t useq = 0;
+    long long row = blockIdx.x;
+    int cnt_next = 0;
+    if (row < p.n_rows) cnt_next = (int)(__ldg(p.row_ptr + row + 1) - __ldg(p.row_ptr + row));
+    for (; row < p.n_rows; row += row_step) {
+      const int cnt = cnt_next;
+      const long long nrow = row + row_step;
+      if (nrow < p.n_rows) cnt_next = (int)(__ldg(p.row_ptr + nrow + 1) - __ldg(p.row_ptr + nrow));
+      if (cnt == 0) continue;
+      const int nst = (cnt + E - 1) / E;
+      for (int st0 = 0; st0 < nst; st0 += kSegStages, gseg++) {
+        const int n = (nst - st0 < kSegStages) ? nst - st0 : kSegStages;
+        const uint32_t a = gseg % kAccSlots;
+        mbar_wait_id(&acc_empty[a], ((gseg / kAccSlots) & 1) ^ 1, 2);
+        const uint32_t d_tmem = tmem_base + a * (uint32_t)G::kN;
+        for (int t = 0; t < n; t++) {
+          mbar_wait_addr(full_a, par);
+          tc_fence_after_sync();
+          umma::mma_bf16_ss_same_elect(d_tmem, dlo, dhi, idesc, (t > 0) ? 1u : 0u);
+          umma::mma_commit_addr_elect(empty_a);  // frees the operand stage once the MMA has read it
+          slot++; full_a += 8; empty_a += 8; dlo += (uint32_t)(G::kBytes >> 4);
+          if (slot == kStages) {
+            slot = 0; par ^= 1u;
+            full_a -= 8 * kStages; empty_a -= 8 * kStages; dlo -= (uint32_t)(kStages * (G::kBytes >> 4));
+          }
+        }
+        umma::mma_commit_elect(&acc_full[a]);  // accumulator segment complete
+      }
+      // every stage of the row has been seen full: the producers' rhs partials are in place
+      if (lane == 0) mbar_arrive(&b_full[useq % kCholWarps]);
+      __syncwarp();
+      useq++;
+    }
+   }
+  } else if (warp < kDrainWarps) {
+    // =========================== drain warpgroup =====================================
+    // Warp qd owns TMEM lane quarter qd = matrix rows 16qd..16qd+15 (lanes +0..15: hi operand
+    // rows, +16..31: lo rows); D's column group fc (32 columns) = [hi | lo] of features
+    // 16fc..16fc+15.  Block (qd, fc), fc <= qd, of W = the sum of the four hi/lo quadrants.
+    umma::reg_dealloc<kRegsDrain>();
+    const int qd = warp;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t lane_hi = (uint32_t)(32 * qd) << 16, lane_lo = (uint32_t)(32 * qd + 16) << 16;
+    const bool has_diag = (t == (g >> 1));
+    const int cfr_off = g * kPS + 2 * t;
+    uint32_t gseg = 0;
+    int useq = 0;
+    for (long long rb = blockIdx.x; rb < p.n_rows; rb += 32 * row_step) {
+      int cnt_l = 0;
+      {
+        const long long myrow = rb + lane * row_step;
+        if (myrow < p.n_rows) cnt_l = (int)(p.row_ptr[myrow + 1] - p.row_ptr[myrow]);
+      }
+      const long long left = (p.n_rows - rb + row_step - 1) / row_step;
+      const int nb = left < 32 ? (int)left : 32;
+      for (int ib = 0; ib < nb; ib++) {
+        const int cnt = __shfl_sync(kFull, cnt_l, ib);
+        if (cnt == 0) continue;
+        const int nst = (cnt + E - 1) / E;
+        const int nseg = (nst + kSegStages - 1) / kSegStages;
+        const int ws = useq % kCholWarps;
+        float* slot = slots + ws * WP::kFloats;
+        // W = G + lambda*alpha*n_u*I + ... (ALS.java:447-450, 488-492); padding rows (>= k) get a
+        // unit diagonal so the factorisation stays finite.  Rows g and g+8 of the block:
+        const float lam_n = (float)(p.lambda_alpha * (double)cnt);
+        const float lam0 = (16 * qd + g < k) ? lam_n : 1.f;
+        const float lam1 = (16 * qd + g + 8 < k) ? lam_n : 1.f;
+        mbar_wait_id(&w_empty[ws], (uint32_t)(((useq / kCholWarps) & 1) ^ 1), 4);
+        for (int seg = 0; seg < nseg; seg++, gseg++) {
+          const int a = (int)(gseg % kAccSlots);
+          mbar_wait_id(&acc_full[a], (gseg / kAccSlots) & 1, 5);
+          tc_fence_after_sync();
+          const uint32_t tcol = tmem_base + (uint32_t)(a * G::kN);
+          const float* src = (seg == 0) ? ng : slot;  // later segments add to what this thread stored
+#pragma unroll
+          for (int fc = 0; fc < 4; fc++) {
+            if (fc > qd) break;  // warp-uniform: block right of the diagonal
+            uint32_t r[16], s[16];
+            tmem_ld_16x256b_x4(tcol + lane_hi + 32 * fc, r);
+            tmem_ld_16x256b_x4(tcol + lane_lo + 32 * fc, s);
+            umma::tmem_wait_ld();
+            float wv[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+              wv[e] = (__uint_as_float(r[e]) + __uint_as_float(r[8 + e])) +
+                      (__uint_as_float(s[e]) + __uint_as_float(s[8 + e]));
+            // wv[4i+0..1]: row g, columns 8i+2t, +1; wv[4i+2..3]: row g+8
+            const int boff = WP::panel_off(fc) + 16 * (qd - fc) * kPS + cfr_off;
+            float2 o[4];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              const float2 n0 = *reinterpret_cast<const float2*>(src + boff + 8 * i);
+              const float2 n1 = *reinterpret_cast<const float2*>(src + boff + 8 * kPS + 8 * i);
+              o[2 * i] = make_float2(n0.x - wv[4 * i], n0.y - wv[4 * i + 1]);
+              o[2 * i + 1] = make_float2(n1.x - wv[4 * i + 2], n1.y - wv[4 * i + 3]);
+            }
+            if (fc == qd && seg == 0 && has_diag) {
+              // diagonal entries: row g at column g (i = 0), row g+8 at column g+8 (i = 1)
+              if (g & 1) { o[0].y -= lam0; o[3].y -= lam1; }
+              else { o[0].x -= lam0; o[3].x -= lam1; }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              *reinterpret_cast<float2*>(slot + boff + 8 * i) = o[2 * i];
+              *reinterpret_cast<float2*>(slot + boff + 8 * kPS + 8 * i) = o[2 * i + 1];
+            }
+          }
+          tc_fence_before_sync();
+          mbar_arrive(&acc_empty[a]);  // accumulator may be overwritten by the next segment
+        }
+        mbar_arrive(&w_full[ws]);  // 128 arrivals: the slot of this row is complete
+        useq++;
+      }
+    }
+  } else {
+    // =========================== Cholesky warps ======================================
+    if constexpr (kRegsChol > 96) umma::reg_alloc<kRegsChol>();
+    const int cw = warp - kFirstChol;
+    float* slot = slots + cw * WP::kFloats;
+    float* scratch = reinterpret_cast<float*>(smem + S::off_scratch) + cw * CB::kScratch;
+    int useq = 0;
+    uint32_t base = 0;
+    for (long long rb = blockIdx.x; rb < p.n_rows; rb += 32 * row_step) {
+      RowBatch B;
+      load_batch<E>(p, rb, row_step, lane, base, B);
+      // flat index of my row's first stage modulo the number of producers: producer
+      // (start + s) % P owns stage s of the row
+      const int nst_l = (B.cnt + E - 1) / E;
+      const int smod_l = (int)((B.end - (uint32_t)nst_l) % (uint32_t)P);
+      for (int ib = 0; ib < B.nb; ib++) {
+        const int cnt = __shfl_sync(kFull, B.cnt, ib);
+        if (cnt == 0) continue;
+        if (useq % kCholWarps != cw) { useq++; continue; }
+        const long long row = rb + ib * row_step;
+        const int nst = (cnt + E - 1) / E;
+        const int smod = __shfl_sync(kFull, smod_l, ib);
+        const uint32_t ph = (uint32_t)((useq / kCholWarps) & 1);
+        mbar_wait_id(&b_full[cw], ph, 7);
+        float b[CB::kS];
+#pragma unroll
+        for (int s = 0; s < CB::kS; s++) b[s] = 0.f;
+#pragma unroll
+        for (int w = 0; w < P; w++) {
+          int rel = w - smod;
+          if (rel < 0) rel += P;
+          if (rel < nst) {  // producer w had a stage in this row
+            const float* bp = bpart + (cw * P + w) * KS;
+#pragma unroll
+            for (int s = 0; s < CB::kS; s++) b[s] += bp[lane + 32 * s];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&b_empty[cw]);
+        mbar_wait_id(&w_full[cw], ph, 6);
+        if (ALS_V2_LOCKSTEP) bar_sync(1, kCholWarps * 32);
+#ifdef ALS_DEBUG_SLOT
+        // development builds only (scripts/v2_debug.py): copy the slot (N = -W_u) and the rhs of
+        // one row out before the solve touches them
+        if (p.row_offset + row == g_debug_row) {
+          for (int e = lane; e < WP::kFloats; e += 32) g_debug_slot[e] = slot[e];
+#pragma unroll
+          for (int s = 0; s < CB::kS; s++) g_debug_slot[WP::kFloats + lane + 32 * s] = b[s];
+          __syncwarp();
+        }
+#endif
+        const float dmax = CB::diag_max(slot, lane, k);
+        const bool ok = CB::factor_solve(slot, scratch, b, dmax, p.threshold, kCondLimit, lane, k);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&w_empty[cw]);
+        if (ok) {
+          float* dst = p.out + (p.row_offset + row) * KS;
+#pragma unroll
+          for (int s = 0; s < CB::kS; s++) {
+            const int r = lane + 32 * s;
+            if (r < k) dst[r] = b[s];
+          }
+        } else if (lane == 0) {
+          const int rs = atomicAdd(p.retry_count, 1);
+          p.retry_rows[rs] = (int)row;
+        }
+        useq++;
+      }
+      base = B.batch_end;
+    }
+    // tail: warps without a row in the last round still meet the others at the barrier
+    if (ALS_V2_LOCKSTEP && (useq % kCholWarps) != 0 && cw >= (useq % kCholWarps))
+      bar_sync(1, kCholWarps * 32);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) umma::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace v2
+
+template <int KS, int NCHOL>
+inline int launch_row_update_v2_t(const RowUpdateParams& p, int sm_count, cudaStream_t stream, char* err,
+                                  size_t err_len) {
+  using S = v2::Smem<KS, NCHOL>;
+  long long grid = sm_count;
+  if (grid > p.n_rows) grid = p.n_rows > 0 ? p.n_rows : 1;
+  v2::row_update_v2_kernel<KS, NCHOL><<<(int)grid, v2::kThreads, S::kTotal, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(err, err_len, "row_update_v2 launch: %s", cudaGetErrorString(e));
+    return ALS_E_CUDA;
+  }
+  return ALS_OK;
+}
+
+}  // namespace als

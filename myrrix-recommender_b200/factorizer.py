@@ -133,6 +133,8 @@ class NativeALS:
         val = np.ascontiguousarray(val, dtype=np.float32)
         if col_idx.size and (col_idx.min() < 0 or col_idx.max() >= n_items):
             raise ValueError("column index out of range")
+        if row_ptr.size < 1 or row_ptr[0] != 0 or np.any(np.diff(row_ptr) < 0):
+            raise ValueError("row_ptr must start at 0 and be non-decreasing")
         self.check(self.lib.als_set_interactions(
             self.h, n_users, n_items, row_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
             col_idx.ctypes.data_as(C.POINTER(C.c_int32)), _fp(val)))
@@ -141,10 +143,21 @@ class NativeALS:
             cp = np.ascontiguousarray(cp, dtype=np.int64)
             ri = np.ascontiguousarray(ri, dtype=np.int32)
             cv = np.ascontiguousarray(cv, dtype=np.float32)
+            if ri.size and (ri.min() < 0 or ri.max() >= n_users):
+                raise ValueError("row index out of range")
+            if cp.size < 1 or cp[0] != 0 or np.any(np.diff(cp) < 0):
+                raise ValueError("col_ptr must start at 0 and be non-decreasing")
             self.check(self.lib.als_set_interactions_by_column(
                 self.h, cp.ctypes.data_as(C.POINTER(C.c_int64)),
                 ri.ctypes.data_as(C.POINTER(C.c_int32)), _fp(cv)))
         self.n_users, self.n_items = int(n_users), int(n_items)
+
+    def set_present_empty_rows(self, which, rows):
+        """Rows that are keys of RbyRow (which=0) / RbyColumn (which=1) with no entries left
+        (InputFilesReader.removeSmall): the reference solves them to the zero vector."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        self.check(self.lib.als_set_present_empty_rows(
+            self.h, int(which), rows.ctypes.data_as(C.POINTER(C.c_int32)), rows.size))
 
     def set_interactions_device(self, n_users, n_items, d_row_ptr, d_col_idx, d_val):
         self.check(self.lib.als_set_interactions_device(self.h, n_users, n_items, d_row_ptr,
@@ -181,6 +194,13 @@ class NativeALS:
         if out is None:
             out = np.empty((self.n_items, self.features), dtype=np.float32)
         self.check(self.lib.als_get_y(self.h, _fp(out)))
+        return out
+
+    def get_rows(self, which, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        out = np.empty((rows.size, self.features), dtype=np.float32)
+        self.check(self.lib.als_get_rows(self.h, 0 if which in (0, "x", "X") else 1,
+                                         rows.ctypes.data_as(C.POINTER(C.c_int32)), rows.size, _fp(out)))
         return out
 
     def get_interactions(self, by_column=False):
@@ -473,20 +493,22 @@ class AlternatingLeastSquares(MatrixFactorizer):
                 self.X, self.Y = {}, dict(Ymap)
                 return None
             als.set_interactions(n_users, n_items, r_ptr, r_idx, r_val, by_column=(c_ptr, c_idx, c_val))
+            # keys whose maps were emptied by removeSmall (InputFilesReader.java:202-211) are still
+            # walked by addWorkers (ALS.java:391-410): W = G, b = 0 -> the zero vector, from the
+            # first half on (so they stop feeding X^T X / Y^T Y like in the reference)
+            pe_u = [uindex[u] for u, row in self.RbyRow.items() if len(row) == 0]
+            pe_i = [iindex[it] for it, row in self.RbyColumn.items() if len(row) == 0]
+            if pe_u:
+                als.set_present_empty_rows(0, pe_u)
+            if pe_i:
+                als.set_present_empty_rows(1, pe_i)
             Y0 = np.stack([np.asarray(Ymap[it], dtype=np.float32) for it in item_ids])
             als.set_y(Y0)
 
             def publish():
                 Xd, Yd = als.get_x(), als.get_y()
-                # rows present in RbyRow with no entries solve to 0 (W=G, b=0)
                 self.X = {u: Xd[i].copy() for i, u in enumerate(user_ids)}
-                newY = {}
-                for i, it in enumerate(item_ids):
-                    row = c_full[it]
-                    if it in self.RbyColumn and len(row) == 0:
-                        newY[it] = np.zeros(k, dtype=np.float32)
-                    else:
-                        newY[it] = Yd[i].copy()
+                newY = {it: Yd[i].copy() for i, it in enumerate(item_ids)}
                 if Ymap is self.previousY:  # adopted in place (ALS.java:304-308)
                     for it, v in newY.items():
                         Ymap[it] = v

@@ -299,6 +299,11 @@ typedef struct {
   double alpha, lambda;
   int reconstruct_r, loss_ignores_unspecified;
   double threshold;
+  /* optional: present[u] != 0 marks a row that is a KEY of the reference's map even though it
+   * has no entries (InputFilesReader.removeSmall, :202-211, empties maps without removing
+   * them).  addWorkers walks every map entry (ALS.java:391-410), so such a row is solved with
+   * Wu = YTY (lambda * 0 on the diagonal) and an all-zero right-hand side. NULL = none. */
+  const uint8_t *present;
   /* work queue */
   int64_t next_unit;
   int64_t n_units;
@@ -333,7 +338,7 @@ static void *half_worker(void *arg) {
     for (int64_t u = u0; u < u1; u++) {
       int64_t e0 = job->row_ptr[u], e1 = job->row_ptr[u + 1];
       int64_t nu = e1 - e0; /* ru.size() */
-      if (nu == 0) continue;
+      if (nu == 0 && !(job->present && job->present[u])) continue; /* not a key of the map */
       /* Wu = YTY.copy() or the partial variant (ALS.java:447-450) */
       if (job->loss_ignores_unspecified) {
         transpose_times_self_subset(job->M, job->col_idx + e0, nu, k, Wu);
@@ -382,13 +387,29 @@ done:
   return NULL;
 }
 
+int oracle_als_half_p(const int64_t *row_ptr, const int32_t *col_idx, const float *val,
+                      int64_t n_rows, const float *M, const double *G, int k, double alpha,
+                      double lambda, int reconstruct_r, int loss_ignores_unspecified,
+                      double threshold, int n_threads, float *out, int *apparent_rank,
+                      const uint8_t *present);
+
 int oracle_als_half(const int64_t *row_ptr, const int32_t *col_idx, const float *val,
                     int64_t n_rows, const float *M, const double *G, int k, double alpha,
                     double lambda, int reconstruct_r, int loss_ignores_unspecified,
                     double threshold, int n_threads, float *out, int *apparent_rank) {
+  return oracle_als_half_p(row_ptr, col_idx, val, n_rows, M, G, k, alpha, lambda, reconstruct_r,
+                           loss_ignores_unspecified, threshold, n_threads, out, apparent_rank, NULL);
+}
+
+int oracle_als_half_p(const int64_t *row_ptr, const int32_t *col_idx, const float *val,
+                      int64_t n_rows, const float *M, const double *G, int k, double alpha,
+                      double lambda, int reconstruct_r, int loss_ignores_unspecified,
+                      double threshold, int n_threads, float *out, int *apparent_rank,
+                      const uint8_t *present) {
   if (k <= 0 || n_rows < 0) return ORACLE_E_ARG;
   half_job_t job;
   memset(&job, 0, sizeof(job));
+  job.present = present;
   job.row_ptr = row_ptr; job.col_idx = col_idx; job.val = val; job.M = M; job.G = G;
   job.out = out; job.n_rows = n_rows; job.k = k; job.alpha = alpha; job.lambda = lambda;
   job.reconstruct_r = reconstruct_r; job.loss_ignores_unspecified = loss_ignores_unspecified;
@@ -450,6 +471,15 @@ double oracle_convergence_probe(const float *X, const float *Y, int k, const int
  *   random_y: 1 mirrors the "don't converge after 1 iteration" guard (:253)
  *   test_users/test_items: the convergence sample (all rows when <= 100, RandomUtils.java:207-211)
  * Returns status; *iterations_run = number of completed iterations. */
+int oracle_als_run_p(const int64_t *r_ptr, const int32_t *r_idx, const float *r_val, int64_t n_users,
+                     const int64_t *rt_ptr, const int32_t *rt_idx, const float *rt_val,
+                     int64_t n_items, int k, double alpha, double lambda, int reconstruct_r,
+                     int loss_ignores_unspecified, double threshold, double convergence_threshold,
+                     int max_iterations, int random_y, const int32_t *test_users, int n_tu,
+                     const int32_t *test_items, int n_ti, int n_threads, float *X, float *Y,
+                     int *iterations_run, int *apparent_rank, double *last_convergence_value,
+                     const uint8_t *present_users, const uint8_t *present_items);
+
 int oracle_als_run(const int64_t *r_ptr, const int32_t *r_idx, const float *r_val, int64_t n_users,
                    const int64_t *rt_ptr, const int32_t *rt_idx, const float *rt_val,
                    int64_t n_items, int k, double alpha, double lambda, int reconstruct_r,
@@ -457,6 +487,22 @@ int oracle_als_run(const int64_t *r_ptr, const int32_t *r_idx, const float *r_va
                    int max_iterations, int random_y, const int32_t *test_users, int n_tu,
                    const int32_t *test_items, int n_ti, int n_threads, float *X, float *Y,
                    int *iterations_run, int *apparent_rank, double *last_convergence_value) {
+  return oracle_als_run_p(r_ptr, r_idx, r_val, n_users, rt_ptr, rt_idx, rt_val, n_items, k, alpha,
+                          lambda, reconstruct_r, loss_ignores_unspecified, threshold,
+                          convergence_threshold, max_iterations, random_y, test_users, n_tu,
+                          test_items, n_ti, n_threads, X, Y, iterations_run, apparent_rank,
+                          last_convergence_value, NULL, NULL);
+}
+
+/* Same, with the keys-without-entries masks of RbyRow / RbyColumn (see half_job_t.present). */
+int oracle_als_run_p(const int64_t *r_ptr, const int32_t *r_idx, const float *r_val, int64_t n_users,
+                     const int64_t *rt_ptr, const int32_t *rt_idx, const float *rt_val,
+                     int64_t n_items, int k, double alpha, double lambda, int reconstruct_r,
+                     int loss_ignores_unspecified, double threshold, double convergence_threshold,
+                     int max_iterations, int random_y, const int32_t *test_users, int n_tu,
+                     const int32_t *test_items, int n_ti, int n_threads, float *X, float *Y,
+                     int *iterations_run, int *apparent_rank, double *last_convergence_value,
+                     const uint8_t *present_users, const uint8_t *present_items) {
   size_t kk = (size_t)k * (size_t)k;
   double *G = (double *)malloc(sizeof(double) * kk);
   double *estimates = (double *)calloc((size_t)n_tu * (size_t)n_ti + 1, sizeof(double));
@@ -468,12 +514,14 @@ int oracle_als_run(const int64_t *r_ptr, const int32_t *r_idx, const float *r_va
   if (!G || !estimates) { rc = ORACLE_E_OOM; goto out; }
   for (;;) {
     oracle_transpose_times_self(Y, n_items, k, G);
-    rc = oracle_als_half(r_ptr, r_idx, r_val, n_users, Y, G, k, alpha, lambda, reconstruct_r,
-                         loss_ignores_unspecified, threshold, n_threads, X, apparent_rank);
+    rc = oracle_als_half_p(r_ptr, r_idx, r_val, n_users, Y, G, k, alpha, lambda, reconstruct_r,
+                           loss_ignores_unspecified, threshold, n_threads, X, apparent_rank,
+                           present_users);
     if (rc != ORACLE_OK) break;
     oracle_transpose_times_self(X, n_users, k, G);
-    rc = oracle_als_half(rt_ptr, rt_idx, rt_val, n_items, X, G, k, alpha, lambda, reconstruct_r,
-                         loss_ignores_unspecified, threshold, n_threads, Y, apparent_rank);
+    rc = oracle_als_half_p(rt_ptr, rt_idx, rt_val, n_items, X, G, k, alpha, lambda, reconstruct_r,
+                           loss_ignores_unspecified, threshold, n_threads, Y, apparent_rank,
+                           present_items);
     if (rc != ORACLE_OK) break;
     double conv = oracle_convergence_probe(X, Y, k, test_users, n_tu, test_items, n_ti, estimates);
     if (last_convergence_value) *last_convergence_value = conv;

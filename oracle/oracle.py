@@ -63,6 +63,9 @@ def lib():
                                       C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, f32p,
                                       C.POINTER(C.c_int)]
         L.oracle_als_half.restype = C.c_int
+        u8p = C.POINTER(C.c_uint8)
+        L.oracle_als_half_p.argtypes = L.oracle_als_half.argtypes + [u8p]
+        L.oracle_als_half_p.restype = C.c_int
         L.oracle_convergence_probe.argtypes = [f32p, f32p, C.c_int, i32p, C.c_int, i32p, C.c_int, f64p]
         L.oracle_convergence_probe.restype = C.c_double
         L.oracle_als_run.argtypes = [i64p, i32p, f32p, C.c_int64, i64p, i32p, f32p, C.c_int64,
@@ -71,6 +74,8 @@ def lib():
                                      C.c_int, f32p, f32p, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      f64p]
         L.oracle_als_run.restype = C.c_int
+        L.oracle_als_run_p.argtypes = L.oracle_als_run.argtypes + [u8p, u8p]
+        L.oracle_als_run_p.restype = C.c_int
         _lib = L
     return _lib
 
@@ -134,9 +139,19 @@ def csr_transpose(row_ptr, col_idx, val, n_cols):
     return t_ptr, np.ascontiguousarray(rows[order]), np.ascontiguousarray(val[order])
 
 
+def _mask(present, n):
+    if present is None:
+        return None, None
+    m = np.zeros(n, dtype=np.uint8)
+    m[np.asarray(present, dtype=np.int64)] = 1
+    return m, _p(m, C.c_uint8)
+
+
 def als_half(row_ptr, col_idx, val, M, G, out, alpha=1.0, lam=0.1, reconstruct_r=False,
-             loss_ignores_unspecified=False, threshold=1e-5, n_threads=1):
-    """out[u] = solve(W_u, b_u) for every row u with entries (in place on `out`)."""
+             loss_ignores_unspecified=False, threshold=1e-5, n_threads=1, present=None):
+    """out[u] = solve(W_u, b_u) for every row u with entries (in place on `out`).  `present`:
+    indices of rows without entries that are nevertheless keys of the reference's map
+    (solved as W = G, b = 0, AlternatingLeastSquares.java:391-410)."""
     row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
     col_idx = np.ascontiguousarray(col_idx, dtype=np.int32)
     val = np.ascontiguousarray(val, dtype=np.float32)
@@ -145,10 +160,11 @@ def als_half(row_ptr, col_idx, val, M, G, out, alpha=1.0, lam=0.1, reconstruct_r
     assert out.dtype == np.float32 and out.flags.c_contiguous
     k = M.shape[1]
     rank = C.c_int(0)
-    rc = lib().oracle_als_half(_p(row_ptr, C.c_int64), _p(col_idx, C.c_int32), _p(val, C.c_float),
-                               row_ptr.size - 1, _p(M, C.c_float), _p(G, C.c_double), k, alpha, lam,
-                               int(reconstruct_r), int(loss_ignores_unspecified), threshold,
-                               n_threads, _p(out, C.c_float), C.byref(rank))
+    keep, pm = _mask(present, row_ptr.size - 1)
+    rc = lib().oracle_als_half_p(_p(row_ptr, C.c_int64), _p(col_idx, C.c_int32), _p(val, C.c_float),
+                                 row_ptr.size - 1, _p(M, C.c_float), _p(G, C.c_double), k, alpha, lam,
+                                 int(reconstruct_r), int(loss_ignores_unspecified), threshold,
+                                 n_threads, _p(out, C.c_float), C.byref(rank), pm)
     if rc == E_SINGULAR:
         raise SingularMatrixError(rank.value)
     if rc != OK:
@@ -159,7 +175,7 @@ def als_half(row_ptr, col_idx, val, M, G, out, alpha=1.0, lam=0.1, reconstruct_r
 def als_run(row_ptr, col_idx, val, n_items, Y0, alpha=1.0, lam=0.1, reconstruct_r=False,
             loss_ignores_unspecified=False, threshold=1e-5, convergence_threshold=0.001,
             max_iterations=30, random_y=False, test_users=None, test_items=None, n_threads=1,
-            t_csr=None):
+            t_csr=None, present_users=None, present_items=None):
     """Full AlternatingLeastSquares.call() restatement. Returns (X, Y, iterations, conv)."""
     row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
     col_idx = np.ascontiguousarray(col_idx, dtype=np.int32)
@@ -181,14 +197,16 @@ def als_run(row_ptr, col_idx, val, n_items, Y0, alpha=1.0, lam=0.1, reconstruct_
     test_users = np.ascontiguousarray(test_users, dtype=np.int32)
     test_items = np.ascontiguousarray(test_items, dtype=np.int32)
     its, rank, conv = C.c_int(0), C.c_int(0), C.c_double(float("nan"))
-    rc = lib().oracle_als_run(_p(row_ptr, C.c_int64), _p(col_idx, C.c_int32), _p(val, C.c_float),
+    keep_u, pu = _mask(present_users, n_users)
+    keep_i, pi = _mask(present_items, n_items)
+    rc = lib().oracle_als_run_p(_p(row_ptr, C.c_int64), _p(col_idx, C.c_int32), _p(val, C.c_float),
                               n_users, _p(t_ptr, C.c_int64), _p(t_idx, C.c_int32),
                               _p(t_val, C.c_float), n_items, k, alpha, lam, int(reconstruct_r),
                               int(loss_ignores_unspecified), threshold, convergence_threshold,
                               max_iterations, int(random_y), _p(test_users, C.c_int32),
                               test_users.size, _p(test_items, C.c_int32), test_items.size,
                               n_threads, _p(X, C.c_float), _p(Y, C.c_float), C.byref(its),
-                              C.byref(rank), C.byref(conv))
+                              C.byref(rank), C.byref(conv), pu, pi)
     if rc == E_SINGULAR:
         raise SingularMatrixError(rank.value)
     if rc != OK:

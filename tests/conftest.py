@@ -69,3 +69,29 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     return (float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)),
             float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)))
+
+
+def dense_als_numpy(R, present_u, present_i, Y0, iters, alpha=1.0, lam=0.1):
+    """Independent fp64 restatement with dense numpy solves (NOT the oracle): a row is solved iff
+    it is a key of the map; a key without entries gets W = G, b = 0."""
+    R = np.asarray(R, np.float64)
+    U, I = R.shape
+    Y = np.asarray(Y0, np.float64).copy()
+    X = np.zeros((U, Y.shape[1]))
+    k = Y.shape[1]
+
+    def half(Rm, Mf, out, present):
+        G = (Mf.astype(np.float32).astype(np.float64)).T @ Mf.astype(np.float32).astype(np.float64)
+        for u in range(Rm.shape[0]):
+            nz = np.nonzero(Rm[u])[0]
+            if nz.size == 0 and u not in present:
+                continue
+            ys = Mf[nz]
+            r = Rm[u, nz]
+            W = G + (ys.T * (alpha * np.abs(r))) @ ys + lam * alpha * nz.size * np.eye(k)
+            b = ((1 + alpha * np.abs(r)) * (r > 0))[None, :] @ ys
+            out[u] = np.linalg.solve(W, b.ravel()).astype(np.float32)
+    for _ in range(iters):
+        half(R, Y.astype(np.float32).astype(np.float64), X, present_u)
+        half(R.T, X.astype(np.float32).astype(np.float64), Y, present_i)
+    return X, Y

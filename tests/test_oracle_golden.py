@@ -119,3 +119,32 @@ def test_half_matches_dense_normal_equations():
         W = G + (y.T * (2.0 * np.abs(r))) @ y + 0.05 * 2.0 * len(r) * np.eye(k)
         b = (y.T * np.where(r > 0, 1 + 2.0 * np.abs(r), 0.0)).sum(axis=1)
         assert np.abs(out[u] - np.linalg.solve(W, b)).max() < 1e-6
+
+
+def test_present_but_empty_rows_in_the_oracle_match_a_dense_solve():
+    """Keys of RbyRow / RbyColumn whose maps removeSmall emptied are still solved by the
+    reference (ALS.java:391-410; InputFilesReader.java:202-211): W = G, b = 0 -> zero vector.
+    The oracle's `present` masks against a dense numpy restatement that shares no code with it."""
+    from conftest import dense_als_numpy, dense_to_csr, rel_err
+    from oracle import oracle as O
+    rng = np.random.default_rng(9)
+    U, I, k = 40, 30, 6
+    R = np.zeros((U, I), np.float32)
+    for u in range(U):
+        R[u, rng.choice(I - 2, 7, replace=False)] = rng.integers(1, 6, 7)
+    R[5] = 0
+    R[6] = 0
+    d = rng.standard_normal((I, k))
+    Y0 = (d / np.sqrt((d * d).sum(1))[:, None]).astype(np.float32)
+    ptr, idx, val = dense_to_csr(R)
+    X, Y, its, _ = O.als_run(ptr, idx, val, I, Y0, max_iterations=3, convergence_threshold=1e-12,
+                             present_users=[5, 6], present_items=[I - 2])
+    Xn, Yn = dense_als_numpy(R, {5, 6}, {I - 2}, Y0, 3)
+    assert its == 3 and np.all(X[5] == 0) and np.all(X[6] == 0) and np.all(Y[I - 2] == 0)
+    assert np.array_equal(Y[I - 1], Y0[I - 1])  # stale item: not a key, untouched
+    for a, b in ((X, Xn), (Y, Yn)):
+        fro, mx = rel_err(a, b)
+        assert fro <= 1e-6 and mx <= 1e-6, (fro, mx)
+    # without the masks the rows keep their previous contents (absent from the map)
+    X2, Y2, _, _ = O.als_run(ptr, idx, val, I, Y0, max_iterations=3, convergence_threshold=1e-12)
+    assert np.array_equal(Y2[I - 2], Y0[I - 2])

@@ -8,7 +8,7 @@ reference arithmetic after a fixed iteration count, identical lambda/alpha/k/Y0:
 import numpy as np
 import pytest
 
-from conftest import dense_to_csr, dense_to_maps, random_problem, rel_err
+from conftest import dense_als_numpy, dense_to_csr, dense_to_maps, random_problem, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -424,3 +424,167 @@ def test_build_then_fold_in(M, O):
     for a, b in ((X, Xo), (Y, Yo)):
         fro, mx = rel_err(a, b)
         assert fro <= TOL and mx <= TOL, (fro, mx)
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: the blocked tensor-core solve in isolation, present-but-empty rows, input validation,
+# and parity at the headline scale
+
+
+def _spd(rng, k, cond):
+    q, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    ev = np.logspace(0, np.log10(cond), k)
+    return (q * ev) @ q.T
+
+
+@pytest.mark.parametrize("k", [64, 50, 33, 32, 17, 5])
+def test_blocked_solver_unit(M, k):
+    """chol_blocked.cuh alone (one warp, one dense system) against numpy's fp64 solve: panel
+    factorisation, 3xTF32 mma.sync trailing updates, backward substitution, padding rows."""
+    import ctypes as C
+    lib = M._native.load()
+    fn = lib.als_debug_solve_blocked
+    fn.restype = C.c_int
+    fp = C.POINTER(C.c_float)
+    fn.argtypes = [fp, fp, C.c_int, C.c_float, fp, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(100 + k)
+    for cond in (3.0, 50.0):
+        W = _spd(rng, k, cond) * 40.0
+        b = rng.standard_normal(k) * 7.0
+        W32 = np.ascontiguousarray(W, dtype=np.float32)
+        b32 = np.ascontiguousarray(b, dtype=np.float32)
+        x = np.zeros(k, np.float32)
+        ok = C.c_int(0)
+        assert fn(W32.ctypes.data_as(fp), b32.ctypes.data_as(fp), k, 1e-5, x.ctypes.data_as(fp), C.byref(ok)) == 0
+        ref = np.linalg.solve(W32.astype(np.float64), b32.astype(np.float64))
+        fro, mx = rel_err(x, ref)
+        assert ok.value == 1 and fro <= 2e-5 and mx <= 2e-5, (k, cond, ok.value, fro, mx)
+    # ill-conditioned / indefinite systems are refused (the caller re-solves them in fp64)
+    for W in (_spd(rng, k, 1e6), -np.eye(k)):
+        W32 = np.ascontiguousarray(W, dtype=np.float32)
+        ok = C.c_int(1)
+        x = np.zeros(k, np.float32)
+        b32 = np.ones(k, np.float32)
+        assert fn(W32.ctypes.data_as(fp), b32.ctypes.data_as(fp), k, 1e-5, x.ctypes.data_as(fp), C.byref(ok)) == 0
+        assert ok.value == 0
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_present_but_empty_rows_solve_to_zero_like_the_reference(M, kernel):
+    """A key of RbyRow / RbyColumn whose map removeSmall emptied (InputFilesReader.java:202-211)
+    is still walked by addWorkers (ALS.java:391-410): W = G, b = 0 -> the zero vector after the
+    FIRST half, so it stops feeding X^T X / Y^T Y.  Checked against a dense numpy solve that
+    shares nothing with the oracle or the kernels."""
+    rng = np.random.default_rng(9)
+    U, I, k = 40, 30, 6
+    R = np.zeros((U, I), np.float32)
+    for u in range(U):
+        cols = rng.choice(I - 2, 7, replace=False)       # items I-2, I-1 never occur
+        R[u, cols] = rng.integers(1, 6, 7)
+    R[5] = 0      # user 5: key with an emptied map
+    R[6] = 0      # user 6: likewise
+    by_row, by_col = dense_to_maps(R)
+    by_row[5] = {}
+    by_row[6] = {}
+    by_col[I - 2] = {}                                  # item I-2: present but empty
+    d = rng.standard_normal((I, k))
+    Y0 = (d / np.sqrt((d * d).sum(1))[:, None]).astype(np.float32)
+    prev = {i: Y0[i].copy() for i in range(I)}          # item I-1: stale (not a key of RbyColumn)
+    als = M.AlternatingLeastSquares(by_row, by_col, k, 1e-9, 3, kernel=kernel)
+    als.setPreviousY(prev)
+    als.call()
+    X, Y = als.getX(), als.getY()
+    Xn, Yn = dense_als_numpy(R, {5, 6}, {I - 2}, Y0, 3)
+    assert np.all(X[5] == 0) and np.all(X[6] == 0) and np.all(Y[I - 2] == 0)
+    assert np.array_equal(Y[I - 1], Y0[I - 1])          # stale row untouched
+    Xg = np.stack([X[u] for u in range(U)])
+    Yg = np.stack([Y[i] for i in range(I)])
+    for a, b in ((Xg, Xn), (Yg, Yn)):
+        fro, mx = rel_err(a, b)
+        assert fro <= TOL and mx <= TOL, (fro, mx)
+
+
+def test_upload_validation_rejects_malformed_csr(M):
+    """als_set_interactions* must refuse a non-monotone row_ptr or an out-of-range index with
+    ALS_E_ARG instead of launching gathers on it (raw C-ABI calls: the Python wrapper's own
+    checks are bypassed on purpose)."""
+    import ctypes as C
+    N = M._native
+    with M.NativeALS(8) as als:
+        def call(ptr, idx, val, U=3, I=4):
+            ptr = np.asarray(ptr, np.int64); idx = np.asarray(idx, np.int32); val = np.asarray(val, np.float32)
+            return als.lib.als_set_interactions(als.h, U, I, ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                val.ctypes.data_as(C.POINTER(C.c_float)))
+        assert call([0, 2, 1, 3], [0, 1, 2], [1, 1, 1]) == N.ALS_E_ARG      # not monotone
+        assert call([0, 1, 2, 3], [0, 4, 2], [1, 1, 1]) == N.ALS_E_ARG      # index == n_items
+        assert call([0, 1, 2, 3], [0, -1, 2], [1, 1, 1]) == N.ALS_E_ARG     # negative index
+        assert call([0, 1, 2, 3], [0, 3, 2], [1, 1, 1]) == N.ALS_OK
+        # the handle is still usable after the rejections
+        als.n_users, als.n_items = 3, 4
+        als.set_y(np.eye(4, 8, dtype=np.float32))
+        als.iterate(1)
+        als.sync()
+        assert np.isfinite(als.get_x()).all()
+
+
+def _sampled_rows(als, rows, by_column):
+    ptrs, idxs, vals = [0], [], []
+    for r in rows:
+        p, i, v = als.get_interaction_rows(int(r), 1, by_column=by_column, capacity=1 << 16)
+        idxs.append(i); vals.append(v); ptrs.append(ptrs[-1] + i.size)
+    return np.array(ptrs, np.int64), np.concatenate(idxs), np.concatenate(vals)
+
+
+def test_headline_config_sampled_row_parity(M, O):
+    """BASELINE.json configs[2] at full size (10M x 1M, 100 entries/user, k = 64): after 1.5
+    device iterations re-solve 200 sampled user rows and 50 item rows (1000 entries each: past
+    the 1024-entry accumulation segment for some) on the CPU oracle from the device's own
+    opposite factor and Gramian inputs; each must match to 1e-4."""
+    k, U, I, nnz = 64, 10_000_000, 1_000_000, 100
+    rng = np.random.default_rng(0)
+    with M.NativeALS(k) as als:
+        als.synth_interactions(U, I, nnz, seed=1234567890, neg_fraction=0.05)
+        als.synth_y0(seed=1234567890)
+        als.iterate(1)
+        als.half_x()
+        als.sync()
+        assert als.info().kernel == 2
+        urows = np.sort(rng.choice(U, 200, replace=False))
+        irows = np.sort(rng.choice(I, 50, replace=False))
+        up, ui, uv = _sampled_rows(als, urows, False)
+        ip, ii, iv = _sampled_rows(als, irows, True)
+        Y = als.get_y()
+        X = als.get_x()
+        als.half_y()
+        als.sync()
+        Y2 = als.get_y()
+        retried = als.timings().fp64_retry_rows
+    assert np.isfinite(X).all() and np.isfinite(Y2).all()
+    out = np.zeros((urows.size, k), np.float32)
+    O.als_half(up, ui, uv, Y, O.transpose_times_self(Y), out)
+    fro, mx = rel_err(X[urows], out)
+    assert fro <= TOL and mx <= TOL, ("X", fro, mx)
+    out = np.zeros((irows.size, k), np.float32)
+    O.als_half(ip, ii, iv, X, O.transpose_times_self(X), out, n_threads=8)
+    fro, mx = rel_err(Y2[irows], out)
+    assert fro <= TOL and mx <= TOL, ("Y", fro, mx)
+    assert retried < 1000  # the fp32 fast path carries the workload
+
+
+def test_headline_cutdown_full_parity_five_iterations(M, O):
+    """100k x 20k, 50 entries/user, k = 64 (the cut-down of the headline config),
+    5 % negative strengths, 5 fixed iterations, every row of X and Y against the oracle."""
+    import os
+    from oracle import synth
+    k, U, I, nnz = 64, 100_000, 20_000, 50
+    ptr, idx, val = synth.synth_rows(0, U, I, nnz, seed=1234567890, neg_fraction=0.05)
+    Y0 = synth.unit_rows(I, k, seed=1234567890)
+    Xo, Yo, its, _ = O.als_run(ptr, idx, val, I, Y0, max_iterations=5, convergence_threshold=1e-12,
+                               n_threads=os.cpu_count() or 8)
+    assert its == 5
+    X, Y, used = _run_gpu(M, ptr, idx, val, I, Y0, 5)
+    assert used == 2
+    for name, a, b in (("X", X, Xo), ("Y", Y, Yo)):
+        fro, mx = rel_err(a, b)
+        assert fro <= TOL and mx <= TOL, (name, fro, mx)
