@@ -114,6 +114,11 @@ struct als_handle {
   // multi-GPU
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
+  // peer replicas of X and Y (cudaIpc mappings; entry `rank` is unused): finished rows are pushed
+  // into them from the solve epilogue.  p2p = false -> exchange by ncclAllGather after the kernel.
+  bool p2p = false, p2p_disabled = false;
+  float* peer_X[16] = {nullptr};
+  float* peer_Y[16] = {nullptr};
   // profiling
   bool profile = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -181,12 +186,77 @@ void free_csr(als_handle* h, Csr* c) {
 
 long long block_rows(long long n, int world) { return (n + world - 1) / world; }
 
+void close_peers(als_handle* h) {
+  for (int r = 0; r < 16; r++) {
+    if (h->peer_X[r]) cudaIpcCloseMemHandle(h->peer_X[r]);
+    if (h->peer_Y[r]) cudaIpcCloseMemHandle(h->peer_Y[r]);
+    h->peer_X[r] = h->peer_Y[r] = nullptr;
+  }
+  h->p2p = false;
+}
+
+// Map every other rank's X and Y replica into this process (cudaIpc handles exchanged with one
+// ncclAllGather).  Collective.  Any failure leaves p2p off: the exchange then falls back to
+// ncclAllGather after each kernel.
+int setup_peers(als_handle* h) {
+  close_peers(h);
+  if (!h->comm || h->world < 2 || h->world > 16 || h->p2p_disabled) return ALS_OK;
+  struct Pair { cudaIpcMemHandle_t x, y; int ok; int pad[3]; };
+  Pair mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.ok = cudaIpcGetMemHandle(&mine.x, h->X) == cudaSuccess && cudaIpcGetMemHandle(&mine.y, h->Y) == cudaSuccess;
+  cudaGetLastError();
+  Pair* d_all = nullptr;
+  CU(h, cudaMalloc(&d_all, sizeof(Pair) * h->world));
+  CU(h, cudaMemcpyAsync(d_all + h->rank, &mine, sizeof(Pair), cudaMemcpyHostToDevice, h->stream));
+  ncclResult_t r = g_nccl.AllGather(d_all + h->rank, d_all, sizeof(Pair), ncclChar, h->comm, h->stream);
+  if (r != ncclSuccess) { cudaFree(d_all); return fail(h, ALS_E_NCCL, "ncclAllGather(ipc handles): %s", g_nccl.GetErrorString(r)); }
+  Pair all[16];
+  CU(h, cudaMemcpyAsync(all, d_all, sizeof(Pair) * h->world, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_all);
+  bool ok = true;
+  for (int q = 0; q < h->world; q++) ok = ok && all[q].ok;
+  for (int q = 0; ok && q < h->world; q++) {
+    if (q == h->rank) continue;
+    void *px = nullptr, *py = nullptr;
+    if (cudaIpcOpenMemHandle(&px, all[q].x, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&py, all[q].y, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      if (px) cudaIpcCloseMemHandle(px);
+      ok = false;
+      break;
+    }
+    h->peer_X[q] = (float*)px;
+    h->peer_Y[q] = (float*)py;
+  }
+  // every rank must agree, or some would wait for rows nobody pushes
+  int* d_ok = h->d_flag + 3;
+  const int mine_ok = ok ? 1 : 0;
+  CU(h, cudaMemcpyAsync(d_ok, &mine_ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  r = g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->stream);
+  if (r != ncclSuccess) return fail(h, ALS_E_NCCL, "ncclAllReduce(p2p agreement): %s", g_nccl.GetErrorString(r));
+  int all_ok = 0;
+  CU(h, cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (!all_ok) close_peers(h);
+  else h->p2p = true;
+  return ALS_OK;
+}
+
 int alloc_factors(als_handle* h) {
   // Factor replicas are padded to world * block rows so the per-half all-gather is a
   // plain in-place ncclAllGather of equal blocks.
   const long long ua = block_rows(h->n_users, h->world) * h->world;
   const long long ia = block_rows(h->n_items, h->world) * h->world;
   if (h->X && ua == h->users_alloc && h->Y && ia == h->items_alloc) return ALS_OK;
+  if (h->p2p) {
+    // collective: every rank re-allocates for the same new sizes; nobody frees a replica while
+    // a peer still has it mapped
+    close_peers(h);
+    g_nccl.AllReduce(h->d_flag + 3, h->d_flag + 3, 1, ncclInt, ncclMin, h->comm, h->stream);
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
   dev_free(h, &h->X, (size_t)h->users_alloc * h->ks);
   dev_free(h, &h->Y, (size_t)h->items_alloc * h->ks);
   h->users_alloc = ua;
@@ -196,7 +266,7 @@ int alloc_factors(als_handle* h) {
   if ((rc = dev_alloc(h, &h->Y, (size_t)ia * h->ks)) != ALS_OK) return rc;
   CU(h, cudaMemsetAsync(h->X, 0, sizeof(float) * (size_t)ua * h->ks, h->stream));
   CU(h, cudaMemsetAsync(h->Y, 0, sizeof(float) * (size_t)ia * h->ks, h->stream));
-  return ALS_OK;
+  return setup_peers(h);
 }
 
 // local block of `n` rows owned by this rank
@@ -370,8 +440,8 @@ int configure_kernels(als_handle* h) {
   } else if (h->ks == 64) {
     if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<64, 4>, umma::Smem<64, 4>::kTotal)) != ALS_OK) return rc;
     if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<64, 8>, umma::Smem<64, 8>::kTotal)) != ALS_OK) return rc;
-    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<64, 4>, v2::Smem<64, 4>::kTotal)) != ALS_OK) return rc;
-    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<64, 8>, v2::Smem<64, 8>::kTotal)) != ALS_OK) return rc;
+    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<64, v2::MixLong>, v2::Smem<64, v2::MixLong>::kTotal)) != ALS_OK) return rc;
+    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<64, v2::MixShort>, v2::Smem<64, v2::MixShort>::kTotal)) != ALS_OK) return rc;
   }
   return ALS_OK;
 }
@@ -400,6 +470,12 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
   p.solve_empty = 0;
   p.retry_rows = nullptr;
   p.retry_count = nullptr;
+  p.n_peers = 0;
+  if (h->p2p) {
+    float* const* peers = which == 0 ? h->peer_X : h->peer_Y;
+    for (int r = 0; r < h->world; r++)
+      if (r != h->rank) p.peer_out[p.n_peers++] = peers[r];
+  }
   CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned long long), h->stream));
   int rc = ALS_OK;
   if (h->kernel == ALS_KERNEL_TCGEN05) {
@@ -420,8 +496,8 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
     const bool long_rows = h->mix_override ? (h->mix_override == 4)
                                            : (R.rows > 0 && R.nnz / R.rows >= kLongRowEntries);
     if (h->ks == 64 && !h->legacy_umma) {
-      rc = long_rows ? launch_row_update_v2_t<64, 4>(p, h->sm_count, h->stream, h->err, sizeof(h->err))
-                     : launch_row_update_v2_t<64, 8>(p, h->sm_count, h->stream, h->err, sizeof(h->err));
+      rc = long_rows ? launch_row_update_v2_t<64, v2::MixLong>(p, h->sm_count, h->stream, h->err, sizeof(h->err))
+                     : launch_row_update_v2_t<64, v2::MixShort>(p, h->sm_count, h->stream, h->err, sizeof(h->err));
     } else {
       rc = launch_row_update_umma(h->ks, p, long_rows, h->sm_count, h->stream, h->err, sizeof(h->err));
     }
@@ -461,6 +537,10 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
 
 int exchange(als_handle* h, float* F, long long n_global) {
   if (h->world == 1 || !h->comm) return ALS_OK;
+  // p2p: the row-update kernels already stored every finished row into all replicas.  The next
+  // half starts with the Gramian all-reduce, which no rank leaves before every rank has
+  // finished (and thereby flushed) its row update: no further synchronisation is needed here.
+  if (h->p2p) return ALS_OK;
   cudaEvent_t a;
   prof_begin(h, &a);
   const long long b = block_rows(n_global, h->world);
@@ -634,12 +714,17 @@ __global__ void debug_solve_blocked_kernel(const float* __restrict__ W, const fl
   float bv[CB::kS];
 #pragma unroll
   for (int s = 0; s < CB::kS; s++) bv[s] = (lane + 32 * s < k) ? b[lane + 32 * s] : 0.f;
+  const long long t0 = clock64();
   const float dmax = CB::diag_max(slot, lane, k);
   const bool good = CB::factor_solve(slot, scratch, bv, dmax, threshold, v2::kCondLimit, lane, k);
+  const long long t1 = clock64();
 #pragma unroll
   for (int s = 0; s < CB::kS; s++)
     if (lane + 32 * s < k) x[lane + 32 * s] = bv[s];
-  if (lane == 0) *ok = good ? 1 : 0;
+  if (lane == 0) {
+    ok[0] = good ? 1 : 0;
+    ok[1] = (int)(t1 - t0);  // cycles of one solve on an otherwise idle SM
+  }
 }
 
 // ===========================================================================
@@ -703,6 +788,7 @@ int als_create(const als_config* cfg, als_handle** out) {
     if (v == 4 || v == 8) h->mix_override = v;
   }
   if (const char* e = getenv("MYRRIX_ALS_V1")) h->legacy_umma = atoi(e) != 0;
+  if (const char* e = getenv("MYRRIX_ALS_NO_P2P")) h->p2p_disabled = atoi(e) != 0;
   CU(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   int rc;
@@ -732,6 +818,14 @@ int als_destroy(als_handle* h) {
   cudaStreamSynchronize(h->stream);
   prof_drain(h);
   free(h->pending);
+  if (h->p2p) {
+    // nobody frees a replica while a peer still has it mapped
+    close_peers(h);
+    if (h->comm && h->d_flag) {
+      g_nccl.AllReduce(h->d_flag + 3, h->d_flag + 3, 1, ncclInt, ncclMin, h->comm, h->stream);
+      cudaStreamSynchronize(h->stream);
+    }
+  }
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   free_csr(h, &h->by_user);
   free_csr(h, &h->by_item);
@@ -1199,19 +1293,33 @@ int als_get_interaction_rows(als_handle* h, int32_t by_column, int64_t first_row
 // ---- development entry points (not part of include/myrrix_als.h) ------------------------------
 // One warp runs the blocked Cholesky (chol_blocked.cuh) on a caller-supplied dense system:
 // checks the solver in isolation from the gather / tensor-core / drain pipeline.
+#ifdef ALS_SOLVE_PROF
+int als_debug_solve_prof(long long* out8) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, als::g_solve_prof, sizeof(long long) * 8);
+  long long z[8] = {0};
+  cudaMemcpyToSymbol(als::g_solve_prof, z, sizeof(z));
+  return 0;
+}
+#endif
+static int g_debug_solve_cycles = 0;
+int als_debug_last_solve_cycles(void) { return g_debug_solve_cycles; }
 int als_debug_solve_blocked(const float* W, const float* b, int k, float threshold, float* x, int* ok) {
   if (!W || !b || !x || !ok || k < 1 || k > 64) return ALS_E_ARG;
   float *dW = nullptr, *db = nullptr, *dx = nullptr;
   int* dok = nullptr;
   cudaMalloc(&dW, sizeof(float) * k * k); cudaMalloc(&db, sizeof(float) * k);
-  cudaMalloc(&dx, sizeof(float) * k); cudaMalloc(&dok, sizeof(int));
+  cudaMalloc(&dx, sizeof(float) * k); cudaMalloc(&dok, 2 * sizeof(int));
   cudaMemcpy(dW, W, sizeof(float) * k * k, cudaMemcpyHostToDevice);
   cudaMemcpy(db, b, sizeof(float) * k, cudaMemcpyHostToDevice);
   if (k <= 32) debug_solve_blocked_kernel<32><<<1, 32>>>(dW, db, k, threshold, dx, dok);
   else debug_solve_blocked_kernel<64><<<1, 32>>>(dW, db, k, threshold, dx, dok);
   cudaError_t e = cudaDeviceSynchronize();
   cudaMemcpy(x, dx, sizeof(float) * k, cudaMemcpyDeviceToHost);
-  cudaMemcpy(ok, dok, sizeof(int), cudaMemcpyDeviceToHost);
+  int okc[2] = {0, 0};
+  cudaMemcpy(okc, dok, 2 * sizeof(int), cudaMemcpyDeviceToHost);
+  ok[0] = okc[0];
+  g_debug_solve_cycles = okc[1];
   cudaFree(dW); cudaFree(db); cudaFree(dx); cudaFree(dok);
   return e == cudaSuccess ? ALS_OK : ALS_E_CUDA;
 }

@@ -73,18 +73,34 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+#ifdef ALS_SOLVE_PROF
+// development builds: cycles per phase of the last solve (panel factorisation, panel write-back +
+// fragment loads, trailing HMMAs, backward sweep), summed over panels
+__device__ long long g_solve_prof[8];
+#define ALS_SP_MARK(i) do { const long long _t = clock64(); if (lane == 0) g_solve_prof[i] += _t - sp_t; sp_t = clock64(); } while (0)
+#else
+#define ALS_SP_MARK(i) do { } while (0)
+#endif
+
 template <int KS>
 struct CholBlocked {
   static_assert(KS == 32 || KS == 64, "blocked warp Cholesky supports k = 32 or 64");
   using WP = WPanels<KS>;
   static constexpr int kPS = WP::kPS;
   static constexpr int kNP = WP::kNP;
-  static constexpr int kS = KS / 32;  // rows per lane: row = lane + 32 * s
-  static constexpr int kScratch = 32; // floats of per-warp scratch: two 16-float column buffers
+  static constexpr int kS = KS / 32;  // rhs / solution entries per lane: row = lane + 32 * s
+  // per-warp scratch (floats): two 16-float column buffers, then the rhs / solution vector
+  static constexpr int kScratch = 32 + KS;
   static constexpr unsigned FULL = 0xffffffffu;
 
   __device__ static __forceinline__ uint32_t smem_addr(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
+  }
+  __device__ static __forceinline__ float get(const float2 (&A)[8], int c) {
+    return (c & 1) ? A[c >> 1].y : A[c >> 1].x;
+  }
+  __device__ static __forceinline__ void set(float2 (&A)[8], int c, float v) {
+    if (c & 1) A[c >> 1].y = v; else A[c >> 1].x = v;
   }
 
   // largest diagonal entry of W_u over the true rows (warp-uniform); w holds N = -W_u
@@ -101,6 +117,131 @@ struct CholBlocked {
     return mine;
   }
 
+  // The 16 column steps of one panel.  Rows are mapped to lanes PER PANEL: lane l holds local
+  // rows l and (TWO) l + 32 of the panel, i.e. matrix rows c0 + l and c0 + l + 32, so the
+  // diagonal block always sits in lanes 0..15 of the first row set and the same code serves
+  // every panel (the panel loop is a run-time loop: ~1.3k instructions of solver code that stay
+  // in the instruction cache, instead of 3.2k of straight-line code per solve).
+  // Each step looks one column ahead: the next pivot (and the next column's update) come
+  // straight out of the owner lane by shuffle as soon as this column's multipliers exist, so the
+  // shared-memory broadcast of the column (needed for the other 14 columns) is off the critical
+  // path: SHFL -> MUFU.RSQ -> FMUL -> FFMA -> SHFL per step.
+  template <bool TWO>
+  __device__ static __forceinline__ void panel_steps(float* pan, int c0, float* ubuf, float* zx, int lane,
+                                                     int k, float dmax, float inv_t, float cond_limit,
+                                                     bool& good) {
+    const int nrows = KS - c0;
+    const bool act0 = lane < nrows;
+    const bool act1 = TWO && (lane + 32 < nrows);
+    float2 a0[8], a1[8];
+    {
+      const float4* s0 = reinterpret_cast<const float4*>(pan + lane * kPS);
+      const float4* s1 = reinterpret_cast<const float4*>(pan + (lane + 32) * kPS);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f), t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act0) v = s0[q];
+        if (act1) t = s1[q];
+        a0[2 * q] = make_float2(v.x, v.y);
+        a0[2 * q + 1] = make_float2(v.z, v.w);
+        a1[2 * q] = make_float2(t.x, t.y);
+        a1[2 * q + 1] = make_float2(t.z, t.w);
+      }
+    }
+    float b0 = act0 ? zx[c0 + lane] : 0.f;
+    float b1 = act1 ? zx[c0 + lane + 32] : 0.f;
+    float myrinv = 1.f;
+    float dcur = -__shfl_sync(FULL, a0[0].x, 0);  // first pivot
+    StaticFor<0, 16>::run([&](auto jc) {
+      constexpr int jj = decltype(jc)::value;
+      const float rinv = rsqrt_fast(dcur);
+      const float mm0 = -get(a0, jj) * rinv;          // L[i][j] of my first row (junk at / above the pivot)
+      const float m0 = (lane > jj) ? mm0 : 0.f;       // 0 for rows at or above the pivot
+      const float m1 = TWO ? -get(a1, jj) * rinv : 0.f;
+      float unext = 0.f;
+      if constexpr (jj < 15) {
+        // look ahead: the next pivot, W[j+1][j+1] - L[j+1][j]^2, exists on lane jj+1 now
+        dcur = -__shfl_sync(FULL, fmaf(mm0, mm0, get(a0, jj + 1)), jj + 1);
+        unext = __shfl_sync(FULL, mm0, jj + 1);       // L[j+1][j], for the next column's update
+      }
+      const float zj = __shfl_sync(FULL, b0, jj) * rinv;
+      if (lane == jj) {
+        myrinv = rinv;
+        b0 = zj;
+        set(a0, jj, rinv);  // the diagonal keeps 1 / L[j][j]
+      } else {
+        b0 = fmaf(-m0, zj, b0);
+        set(a0, jj, m0);
+      }
+      if (TWO) {
+        b1 = fmaf(-m1, zj, b1);
+        set(a1, jj, m1);
+      }
+      if constexpr (jj < 15) {
+        set(a0, jj + 1, fmaf(m0, unext, get(a0, jj + 1)));
+        if (TWO) set(a1, jj + 1, fmaf(m1, unext, get(a1, jj + 1)));
+      }
+      if constexpr (jj < 14) {
+        // columns jj+2 .. 15: the diagonal block's part of column j through shared memory
+        float* buf = ubuf + (jj & 1) * 16;
+        if (lane < 16) buf[lane] = m0;
+        __syncwarp();
+#pragma unroll
+        for (int q = (jj + 2) / 4; q < 4; q++) {
+          const float4 u = *reinterpret_cast<const float4*>(buf + 4 * q);
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int pr = 2 * q + h;  // column pair (2 pr, 2 pr + 1)
+            const float2 uu = h ? make_float2(u.z, u.w) : make_float2(u.x, u.y);
+            if (2 * pr + 1 < jj + 2) continue;
+            if (2 * pr + 1 == jj + 2) {  // only the pair's second column is still open
+              a0[pr].y = fmaf(m0, uu.y, a0[pr].y);
+              if (TWO) a1[pr].y = fmaf(m1, uu.y, a1[pr].y);
+            } else {
+              a0[pr] = ffma2(make_float2(m0, m0), uu, a0[pr]);
+              if (TWO) a1[pr] = ffma2(make_float2(m1, m1), uu, a1[pr]);
+            }
+          }
+        }
+      }
+    });
+    // finished panel back to the slot (L; 1 / L[j][j] on the diagonal), rhs back to the vector
+    {
+      float4* d0 = reinterpret_cast<float4*>(pan + lane * kPS);
+      float4* d1 = reinterpret_cast<float4*>(pan + (lane + 32) * kPS);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (act0) d0[q] = make_float4(a0[2 * q].x, a0[2 * q].y, a0[2 * q + 1].x, a0[2 * q + 1].y);
+        if (act1) d1[q] = make_float4(a1[2 * q].x, a1[2 * q].y, a1[2 * q + 1].x, a1[2 * q + 1].y);
+      }
+      if (act0) zx[c0 + lane] = b0;
+      if (act1) zx[c0 + lane + 32] = b1;
+    }
+    // Judge the pivots of the true rows through 1/sqrt(d): d > threshold <=> rinv^2 < 1/threshold,
+    // dmax / d <= cond_limit <=> dmax * rinv^2 <= cond_limit.  Zero / negative / NaN pivots give
+    // inf / NaN and fail.  (No early exit: the warp stays converged.)
+    if (lane < 16 && c0 + lane < k) {
+      const float r2 = myrinv * myrinv;
+      good = good && myrinv > 0.f && r2 < inv_t && r2 * dmax <= cond_limit;
+    }
+    __syncwarp();
+  }
+
+  // hi/lo tf32 split of one 16-row block of the panel (two k-steps of 8 columns)
+  __device__ static __forceinline__ void load_frags(const float* blk_rows, int ldm_off, uint32_t (&hi)[2][4],
+                                                    uint32_t (&lo)[2][4]) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ks++) {
+      uint32_t raw[4];
+      ldmatrix_x4(smem_addr(blk_rows + 8 * ks + ldm_off), raw);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        hi[ks][e] = raw[e] & 0xffffe000u;
+        lo[ks][e] = __float_as_uint(__uint_as_float(raw[e]) - __uint_as_float(hi[ks][e]));
+      }
+    }
+  }
+
   // w: the slot (N = -W_u on entry).  scratch: kScratch floats private to this warp.
   // b[s]: rhs entry of row lane + 32 s on entry, solution entry on return.  dmax: diag_max()
   // of the slot before the sweep.  k: true feature count; padding rows (>= k) must carry a
@@ -109,183 +250,103 @@ struct CholBlocked {
   __device__ static __forceinline__ bool factor_solve(float* w, float* scratch, float (&b)[kS],
                                                       float dmax, float threshold, float cond_limit,
                                                       int lane, int k) {
-    float rinv_mine[kS];  // 1/sqrt(pivot) of my rows
-#pragma unroll
-    for (int s = 0; s < kS; s++) rinv_mine[s] = 0.f;
+    float* ubuf = scratch;
+    float* zx = scratch + 32;  // rhs -> z = L^-1 b -> x, by matrix row
     const int g = lane >> 2, t = lane & 3;
     // ldmatrix: lane i addresses row (i&7) + 8*((i>>3)&1) of a 16-row block, 16-byte column
     // group (i>>4) of an 8-float k-step
     const int ldm_off = ((lane & 7) + 8 * ((lane >> 3) & 1)) * kPS + 4 * (lane >> 4);
     const int cfr_off = g * kPS + 2 * t;  // accumulator fragment: rows g / g+8, columns 2t, 2t+1 (+8)
+#pragma unroll
+    for (int s = 0; s < kS; s++) zx[lane + 32 * s] = b[s];
+    __syncwarp();
+    bool good = dmax > threshold && isfinite(dmax);
+    const float inv_t = 1.0f / threshold;
+#ifdef ALS_SOLVE_PROF
+    long long sp_t = clock64();
+#endif
 
     // ---- forward: panel factorisation + trailing update --------------------------------------
-    StaticFor<0, kNP>::run([&](auto pc) {
-      constexpr int P = decltype(pc)::value;
-      constexpr int c0 = 16 * P;
-      constexpr int s_min = c0 / 32;  // first slot with active rows
+#pragma unroll 1
+    for (int P = 0; P < kNP; P++) {
+      const int c0 = 16 * P;
       float* pan = w + WP::panel_off(P);
-      float2 a[kS][8];
-      bool act[kS];
+      if (c0 + 32 < KS) panel_steps<true>(pan, c0, ubuf, zx, lane, k, dmax, inv_t, cond_limit, good);
+      else panel_steps<false>(pan, c0, ubuf, zx, lane, k, dmax, inv_t, cond_limit, good);
+      ALS_SP_MARK(1);  // panel: load, 16 column steps, write-back
+      // trailing update on the tensor cores: N[I][J] += L[I][P] L[J][P]^T, P < J <= I; every
+      // product as hi*hi + hi*lo + lo*hi of tf32 splits, in three independent accumulators
+      const int NB = kNP - 1 - P;  // block rows below the diagonal block
+#pragma unroll 1
+      for (int bj = 0; bj < NB; bj++) {
+        uint32_t hiB[2][4], loB[2][4];
+        load_frags(pan + 16 * (bj + 1) * kPS, ldm_off, hiB, loB);
+        float* panJ = w + WP::panel_off(P + 1 + bj);
 #pragma unroll
-      for (int s = s_min; s < kS; s++) {
-        const int row = lane + 32 * s;
-        act[s] = row >= c0;
-        const float4* src = reinterpret_cast<const float4*>(pan + (row - c0) * kPS);
+        for (int dd = 0; dd < kNP - 1; dd++) {  // (unrolled: the next block's loads overlap this block's HMMAs)
+          const int bi = bj + dd;
+          if (bi >= NB) break;
+          uint32_t hiA[2][4], loA[2][4];
+          if (bi == bj) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (act[s]) v = src[q];
-          a[s][2 * q] = make_float2(v.x, v.y);
-          a[s][2 * q + 1] = make_float2(v.z, v.w);
-        }
-      }
-      StaticFor<0, 16>::run([&](auto jc) {
-        constexpr int jj = decltype(jc)::value;
-        constexpr int j = c0 + jj;
-        constexpr int own = j & 31, os = j >> 5;
-        float* buf = scratch + (jj & 1) * 16;
-        const float njj = (jj & 1) ? a[os][jj >> 1].y : a[os][jj >> 1].x;  // -W[.][j] of my row in slot os
-        const float d = -__shfl_sync(FULL, njj, own);                      // pivot
-        const float rinv = rsqrt_fast(d);
-        const float zj = __shfl_sync(FULL, b[os], own) * rinv;
-        float m[kS];
+            for (int ks = 0; ks < 2; ks++)
 #pragma unroll
-        for (int s = s_min; s < kS; s++) {
-          const float nv = (jj & 1) ? a[s][jj >> 1].y : a[s][jj >> 1].x;
-          const bool below = (s > os) || (lane > own);
-          m[s] = below ? -nv * rinv : 0.f;  // L[i][j]; 0 for rows at or above the pivot
-          float keep = m[s];
-          if (s == os && lane == own) {
-            keep = rinv;  // the diagonal keeps 1 / L[j][j]
-            rinv_mine[s] = rinv;
-            b[s] = zj;
+              for (int e = 0; e < 4; e++) { hiA[ks][e] = hiB[ks][e]; loA[ks][e] = loB[ks][e]; }
           } else {
-            b[s] = fmaf(-m[s], zj, b[s]);
+            load_frags(pan + 16 * (bi + 1) * kPS, ldm_off, hiA, loA);
           }
-          if (jj & 1) a[s][jj >> 1].y = keep; else a[s][jj >> 1].x = keep;
-        }
-        if constexpr (jj < 15) {
-          // the diagonal block's part of column j, for everybody
-          if ((lane >> 4) == ((c0 & 31) >> 4)) buf[lane & 15] = m[os];
-          __syncwarp();
+          float* blk = panJ + 16 * (bi - bj) * kPS + cfr_off;
+          float chh[2][4], chl[2][4], clh[2][4];
 #pragma unroll
-          for (int q = (jj + 1) / 4; q < 4; q++) {
-            const float4 u = *reinterpret_cast<const float4*>(buf + 4 * q);
+          for (int nt = 0; nt < 2; nt++) {
+            const float2 v0 = *reinterpret_cast<const float2*>(blk + 8 * nt);
+            const float2 v1 = *reinterpret_cast<const float2*>(blk + 8 * kPS + 8 * nt);
+            chh[nt][0] = v0.x; chh[nt][1] = v0.y; chh[nt][2] = v1.x; chh[nt][3] = v1.y;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-              const int pr = 2 * q + h;  // column pair (2 pr, 2 pr + 1) of the panel
-              const float2 uu = h ? make_float2(u.z, u.w) : make_float2(u.x, u.y);
-              if (2 * pr + 1 <= jj) continue;
+            for (int e = 0; e < 4; e++) { chl[nt][e] = 0.f; clh[nt][e] = 0.f; }
+          }
 #pragma unroll
-              for (int s = s_min; s < kS; s++) {
-                if (2 * pr == jj) a[s][pr].y = fmaf(m[s], uu.y, a[s][pr].y);  // .x is column j itself
-                else a[s][pr] = ffma2(make_float2(m[s], m[s]), uu, a[s][pr]);
-              }
+          for (int ks = 0; ks < 2; ks++) {
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+              // B fragment of n-tile nt = A-fragment registers (nt, nt + 2) of block row bj
+              mma_tf32(chh[nt], hiA[ks][0], hiA[ks][1], hiA[ks][2], hiA[ks][3], hiB[ks][nt], hiB[ks][nt + 2]);
+              mma_tf32(chl[nt], hiA[ks][0], hiA[ks][1], hiA[ks][2], hiA[ks][3], loB[ks][nt], loB[ks][nt + 2]);
+              mma_tf32(clh[nt], loA[ks][0], loA[ks][1], loA[ks][2], loA[ks][3], hiB[ks][nt], hiB[ks][nt + 2]);
             }
           }
-        }
-      });
-      // write the finished panel back (L; 1/L[j][j] on the diagonal)
 #pragma unroll
-      for (int s = s_min; s < kS; s++) {
-        const int row = lane + 32 * s;
-        float4* dst = reinterpret_cast<float4*>(pan + (row - c0) * kPS);
-        if (act[s]) {
-#pragma unroll
-          for (int q = 0; q < 4; q++)
-            dst[q] = make_float4(a[s][2 * q].x, a[s][2 * q].y, a[s][2 * q + 1].x, a[s][2 * q + 1].y);
+          for (int nt = 0; nt < 2; nt++) {
+            *reinterpret_cast<float2*>(blk + 8 * nt) =
+                make_float2(chh[nt][0] + (chl[nt][0] + clh[nt][0]), chh[nt][1] + (chl[nt][1] + clh[nt][1]));
+            *reinterpret_cast<float2*>(blk + 8 * kPS + 8 * nt) =
+                make_float2(chh[nt][2] + (chl[nt][2] + clh[nt][2]), chh[nt][3] + (chl[nt][3] + clh[nt][3]));
+          }
         }
       }
       __syncwarp();
-      if constexpr (P + 1 < kNP) {
-        // trailing update on the tensor cores: N[I][J] += L[I][P] L[J][P]^T, P < J <= I
-        constexpr int NB = kNP - 1 - P;  // block rows below the diagonal block
-        uint32_t hi[NB][2][4], lo[NB][2][4];
-#pragma unroll
-        for (int bi = 0; bi < NB; bi++) {
-#pragma unroll
-          for (int ks = 0; ks < 2; ks++) {
-            uint32_t raw[4];
-            ldmatrix_x4(smem_addr(pan + 16 * (bi + 1) * kPS + 8 * ks + ldm_off), raw);
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              hi[bi][ks][e] = raw[e] & 0xffffe000u;
-              lo[bi][ks][e] = __float_as_uint(__uint_as_float(raw[e]) - __uint_as_float(hi[bi][ks][e]));
-            }
-          }
-        }
-#pragma unroll
-        for (int bj = 0; bj < NB; bj++) {
-          float* panJ = w + WP::panel_off(P + 1 + bj);
-#pragma unroll
-          for (int bi = bj; bi < NB; bi++) {
-            float* blk = panJ + 16 * (bi - bj) * kPS + cfr_off;
-            float c[2][4];
-#pragma unroll
-            for (int nt = 0; nt < 2; nt++) {
-              const float2 v0 = *reinterpret_cast<const float2*>(blk + 8 * nt);
-              const float2 v1 = *reinterpret_cast<const float2*>(blk + 8 * kPS + 8 * nt);
-              c[nt][0] = v0.x; c[nt][1] = v0.y; c[nt][2] = v1.x; c[nt][3] = v1.y;
-            }
-#pragma unroll
-            for (int nt = 0; nt < 2; nt++) {
-#pragma unroll
-              for (int ks = 0; ks < 2; ks++) {
-                // B fragment of n-tile nt = A-fragment registers (nt, nt + 2) of block row bj
-                mma_tf32(c[nt], hi[bi][ks][0], hi[bi][ks][1], hi[bi][ks][2], hi[bi][ks][3],
-                         hi[bj][ks][nt], hi[bj][ks][nt + 2]);
-                mma_tf32(c[nt], hi[bi][ks][0], hi[bi][ks][1], hi[bi][ks][2], hi[bi][ks][3],
-                         lo[bj][ks][nt], lo[bj][ks][nt + 2]);
-                mma_tf32(c[nt], lo[bi][ks][0], lo[bi][ks][1], lo[bi][ks][2], lo[bi][ks][3],
-                         hi[bj][ks][nt], hi[bj][ks][nt + 2]);
-              }
-            }
-#pragma unroll
-            for (int nt = 0; nt < 2; nt++) {
-              *reinterpret_cast<float2*>(blk + 8 * nt) = make_float2(c[nt][0], c[nt][1]);
-              *reinterpret_cast<float2*>(blk + 8 * kPS + 8 * nt) = make_float2(c[nt][2], c[nt][3]);
-            }
-          }
-        }
-        __syncwarp();
-      }
-    });
-
-    // Judge the pivots of the true rows through 1/sqrt(d): d > threshold <=> rinv^2 < 1/threshold,
-    // dmax / d <= cond_limit <=> dmax * rinv^2 <= cond_limit.  Zero / negative / NaN pivots give
-    // inf / NaN and fail.  No early exit: the warp stays converged through the backward sweep.
-    bool good = dmax > threshold && isfinite(dmax);
-    {
-      const float inv_t = 1.0f / threshold;
-#pragma unroll
-      for (int s = 0; s < kS; s++) {
-        const float r2 = rinv_mine[s] * rinv_mine[s];
-        if (lane + 32 * s < k) good = good && rinv_mine[s] > 0.f && r2 < inv_t && r2 * dmax <= cond_limit;
-      }
+      ALS_SP_MARK(3);  // trailing blocks
     }
 
     // ---- backward: x = L^-T z, panel by panel from the last -----------------------------------
-    float x[kS];
-#pragma unroll
-    for (int s = 0; s < kS; s++) x[s] = 0.f;
     const int tt = (lane >> 1) & 15;  // column of the block this lane (pair) finishes
-    StaticFor<kNP - 1, -1, -1>::run([&](auto pc) {
-      constexpr int P = decltype(pc)::value;
-      constexpr int c0 = 16 * P;
+#pragma unroll 1
+    for (int P = kNP - 1; P >= 0; P--) {
+      const int c0 = 16 * P;
       const float* pan = w + WP::panel_off(P);
+      const int nrows = KS - c0;
       float sum = 0.f;  // sum_{i >= c0+16} L[i][c0+tt] x_i
-      if constexpr (P + 1 < kNP) {
-        constexpr int s_lo = (c0 + 16) / 32;
+      if (P + 1 < kNP) {
         float2 acc[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) acc[q] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int s = s_lo; s < kS; s++) {
-          const int row = lane + 32 * s;
-          const bool on = row >= c0 + 16;
-          const float xm = on ? x[s] : 0.f;
+        for (int s = 0; s < kS; s++) {
+          const int lr = lane + 32 * s;  // local row of the panel
+          const bool on = lr >= 16 && lr < nrows;
+          const float xm = on ? zx[c0 + lr] : 0.f;
           const float2 xx = make_float2(xm, xm);
-          const float4* src = reinterpret_cast<const float4*>(pan + (row - c0) * kPS);
+          const float4* src = reinterpret_cast<const float4*>(pan + lr * kPS);
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -313,31 +374,31 @@ struct CholBlocked {
         r1 += __shfl_xor_sync(FULL, r1, 1);
         sum = r1;
       }
-      // z of column c0 + tt sits in the lane that owns that row
-      constexpr int zs = c0 >> 5;
-      float v = __shfl_sync(FULL, b[zs], (c0 & 31) + tt) - sum;
-      // column tt of the diagonal block (rows tt+1..15) and 1/L[tt][tt]
+      ALS_SP_MARK(4);  // rows below the block + butterfly
+      // x_t = dinv_t (z_t - sum_t) - sum_{t' > t} (dinv_t L[t'][t]) x_t': column tt of the diagonal
+      // block pre-scaled by 1 / L[tt][tt], so each of the 16 steps is one shuffle + one FMA
+      const float dinv = pan[tt * kPS + tt];
+      float v = (zx[c0 + tt] - sum) * dinv;
       float col[16];
 #pragma unroll
-      for (int tp = 1; tp < 16; tp++) col[tp] = pan[tp * kPS + tt];
-      const float dinv = pan[tt * kPS + tt];
+      for (int tp = 1; tp < 16; tp++) col[tp] = pan[tp * kPS + tt] * dinv;
       float xmine = 0.f;
 #pragma unroll
       for (int tp = 15; tp >= 0; tp--) {
-        const float xt = __shfl_sync(FULL, v * dinv, 2 * tp);  // x_{c0+tp}, final on its lane pair
+        const float xt = __shfl_sync(FULL, v, 2 * tp);  // x_{c0+tp}, final on its lane pair
         if (tt == tp) xmine = xt;
         if (tp > 0) v = fmaf(-col[tp], xt, v);  // lanes tt >= tp read junk here; their x is already taken
       }
-      // hand the block's solution to the row owners
-      const int src = 2 * ((lane - (c0 & 31)) & 15);
-      const float xo = __shfl_sync(FULL, xmine, src);
-      if ((lane >> 4) == ((c0 & 31) >> 4)) x[zs] = xo;
-    });
+      __syncwarp();  // every lane has read z of this block
+      if ((lane & 1) == 0) zx[c0 + tt] = xmine;
+      __syncwarp();
+      ALS_SP_MARK(5);  // in-block triangular solve
+    }
     bool fin = true;
 #pragma unroll
     for (int s = 0; s < kS; s++) {
-      fin = fin && isfinite(x[s]);
-      b[s] = x[s];
+      b[s] = zx[lane + 32 * s];
+      fin = fin && isfinite(b[s]);
     }
     return __all_sync(FULL, good && fin);
   }

@@ -23,6 +23,8 @@
 
 namespace als {
 
+constexpr int kMaxPeers = 15;  // other ranks of one NVSwitch domain
+
 struct RowUpdateParams {
   const long long* row_ptr;  // CSR of this orientation, local rows [0, n_rows]
   const int* col_idx;
@@ -50,7 +52,17 @@ struct RowUpdateParams {
   // Filled by the tensor-core kernel: rows it refused (singular / ill-conditioned in fp32).
   int* retry_rows;
   int* retry_count;
+  // Multi-GPU: the other ranks' replicas of `out` (peer memory over NVLink).  Every finished row
+  // is stored into all of them from the solve epilogue, so the factor exchange overlaps the
+  // kernel instead of following it.  n_peers = 0: single GPU / exchange by NCCL.
+  int n_peers;
+  float* peer_out[kMaxPeers];
 };
+
+// One thread's element of a finished row -> every peer replica.
+__device__ __forceinline__ void push_to_peers(const RowUpdateParams& p, long long elem_offset, float v) {
+  for (int r = 0; r < p.n_peers; r++) p.peer_out[r][elem_offset] = v;
+}
 
 constexpr int kSimtThreads = 128;
 constexpr int kSimtChunk = 32;  // gathered rows staged per step
@@ -213,6 +225,10 @@ row_update_simt_kernel(const RowUpdateParams p) {
     // fp64 LDL^T + solves (first barrier inside covers the W / bvec writes above)
     ldlt_solve_fp64<KS>(W, bvec, invd, k, tid, 0, (double)p.threshold, p.status, p.which,
                         p.row_offset + row, p.out + (p.row_offset + row) * KS);
+    if (p.n_peers > 0) {
+      __syncthreads();  // the row as the solve left it (untouched if it failed)
+      if (tid < k) push_to_peers(p, (p.row_offset + row) * KS + tid, p.out[(p.row_offset + row) * KS + tid]);
+    }
   }
 }
 

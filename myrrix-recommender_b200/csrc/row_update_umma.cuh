@@ -606,7 +606,10 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_umma_kernel(const RowU
 #pragma unroll
           for (int s = 0; s < CW::kRowsPerLane; s++) {
             const int r = CW::row_of(lane, s);
-            if (CW::writes(lane, s) && r < k) dst[r] = bx[s];
+            if (CW::writes(lane, s) && r < k) {
+              dst[r] = bx[s];
+              push_to_peers(p, (p.row_offset + row) * KS + r, bx[s]);
+            }
           }
         } else if (lane == 0) {
           const int slot = atomicAdd(p.retry_count, 1);

@@ -6,14 +6,29 @@
 // instructions per solved row, issue slots and the shared-memory pipe saturated long before
 // HBM):
 //
-//   producers   own every P-th 16-entry stage of the CTA's flat stage stream like before, but
-//               find their stage with one ballot over a per-batch prefix sum of the rows' stage
-//               counts (no per-row cursor walk, no integer modulo), do the per-entry scalar work
-//               (index, sqrt(alpha |r|), rhs weight) once per entry on one lane and hand it to
-//               the 16 lanes of the entry by shuffle, prefetch the next stage's indices / values
-//               while the gathers are in flight, and address the swizzled operand slots as
-//               (lane base) ^ (per-pass constant).  Each producer keeps the partial rhs of ITS
-//               stages of a row in registers and writes it once, when it leaves the row.
+//   producers   (7 or 11 warps) own every P-th 16-entry stage of the CTA's flat stage stream.
+//               GATHER: asynchronous 16-byte copies (cp.async: no register staging, zero-fill
+//               beyond a row's last entry) of the fp32 factor rows straight into the operand
+//               ring slot of the stage, completion signalled on the slot's mbarrier
+//               (cp.async.mbarrier.arrive); every producer keeps the gathers of its next kAhead
+//               stages in flight while it converts the current one, so the ring is the in-flight
+//               buffer: ~55-90 KB of gathers outstanding per SM with no registers tied up (round
+//               1 held 7-11 warps x 4 KB in registers and was latency-bound at 1.5 / 4 TB/s).
+//               CONVERT in place: read the raw fp32 rows back from the slot (16-byte loads,
+//               conflict-free), scale by sqrt(alpha |r|), split into bf16 hi + bf16 lo, write the
+//               swizzled MN-major operand tile into the same 4 KB.  Stage lookup is one ballot
+//               over a per-batch prefix sum of the rows' stage counts (no cursor walk, no integer
+//               modulo); per-entry scalars once per entry on one lane, handed to the 16 lanes of
+//               the entry by shuffle; swizzled slots addressed as (lane base) ^ (per-pass
+//               constant).  Each producer keeps the partial rhs of ITS stages of a row in
+//               registers and writes it once, when it leaves the row.
+//               Measured alternatives: a dedicated loader warp issuing the same
+//               copies (one warp cannot keep enough of them in flight: 1.9 TB/s), and per-row TMA
+//               bulk copies (cp.async.bulk takes its addresses from uniform registers, so 32
+//               divergent rows serialise into 32 elect / R2UR round trips per warp: 0.9 TB/s).
+//               TMA bulk copies are used where addresses are warp-uniform: the finished factor
+//               rows (Cholesky epilogue).  -DALS_V2_TMA=0 builds the register-gather producers
+//               (LDG.128 + the same conversion) for A/B runs.
 //   MMA issuer  unchanged (one tcgen05.mma per stage, D += [hi;lo][hi;lo]^T); it also signals
 //               "rhs complete" for a row after it has seen the row's last stage.
 //   drain       reads the accumulator with tcgen05.ld.16x256b: the register layout is the
@@ -44,8 +59,6 @@ using umma::tc_fence_before_sync;
 
 constexpr int kDrainWarps = 4;                 // warps 0..3 (TMEM lane quarters)
 constexpr int kFirstChol = kDrainWarps;
-constexpr int kMmaWarp = 19;
-constexpr int kThreads = (kMmaWarp + 1) * 32;  // 640
 constexpr int kAccSlots = 4;
 constexpr int kSegStages = 64;
 constexpr int kTmemCols = 512;
@@ -56,39 +69,86 @@ constexpr int kRegsDrain = 64;
 constexpr int kRegsChol = ALS_V2_REGS_CHOL;
 constexpr float kCondLimit = 256.f;  // max diag / min pivot above which a row goes to fp64
 constexpr unsigned kFull = 0xffffffffu;
+// Cholesky warps enter each sweep together in groups (one instruction stream per group for the
+// ~50 KB of straight-line solver code): 1 = all warps of the CTA, 2 / 4 = that many staggered
+// groups (while one group solves, the drain refills the slots of the other), 0 = no grouping.
 #ifndef ALS_V2_LOCKSTEP
-#define ALS_V2_LOCKSTEP 1
+#define ALS_V2_LOCKSTEP 2
 #endif
+// W slots beyond one per Cholesky warp (8-warp mix): the solve runs in place, so a slot is busy
+// for the whole solve; spare slots let the drain work ahead of the oldest unfinished solve.
+#ifndef ALS_V2_XSLOTS
+#define ALS_V2_XSLOTS 0
+#endif
+
+// 1: asynchronous gathers into the ring by a loader warp, in-place conversion; 0: register gathers (LDG)
+#ifndef ALS_V2_TMA
+#define ALS_V2_TMA 1
+#endif
+constexpr bool kTma = ALS_V2_TMA != 0;
 
 #ifdef ALS_DEBUG_SLOT
 __device__ long long g_debug_row = -1;
 __device__ float g_debug_slot[WPanels<64>::kFloats + 64];
 #endif
 
-template <int NCHOL>
+// Role mix of one CTA: 4 drain warps | NCHOL Cholesky warps | NPROD producer warps | 1 MMA warp.
+//   STAGES  operand ring depth (4 KB each); with asynchronous gathers the ring is also the
+//           in-flight buffer: (AHEAD + 1) * NPROD slots are in flight or being converted
+//   AHEAD   own-stages whose gathers a producer keeps in flight
+//   SETREG  re-balance registers between the roles with setmaxnreg (needs whole warpgroups per
+//           role); otherwise every role lives within the launch register count
+template <int NCHOL, int NPROD, int STAGES, int AHEAD, bool SETREG>
 struct Mix {
-  static_assert(NCHOL == 8 || NCHOL == 4, "whole warpgroups per role");
   static constexpr int kCholWarps = NCHOL;
-  static constexpr int kProdWarps = 15 - NCHOL;
+  static constexpr int kProdWarps = NPROD;
   static constexpr int kFirstProd = kFirstChol + NCHOL;
-  static constexpr int kStages = (NCHOL == 8) ? 16 : 24;  // operand ring depth (4 KB each)
-  static constexpr int kRegsProd = (NCHOL == 8) ? 80 : 96;
-  static_assert(32 * (kRegsDrain + (NCHOL / 4) * kRegsChol + ((16 - NCHOL) / 4) * kRegsProd) <= 5 * 96 * 32,
+  static constexpr int kMmaWarp = kFirstProd + NPROD;
+  static constexpr int kThreads = 32 * (kMmaWarp + 1);
+  static constexpr int kStages = STAGES;
+  static constexpr int kAhead = AHEAD;
+  static constexpr int kWSlots = NCHOL;                 // the solve runs in place: one slot per Cholesky warp
+  static constexpr int kBSlots = NCHOL < 8 ? NCHOL : 8;  // rhs ring (row u -> slot u % kBSlots)
+  static constexpr bool kSetReg = SETREG;
+  static constexpr int kRegsProd = (kThreads == 640 && NCHOL == 8) ? 80 : 96;
+  static_assert(kThreads <= 1024, "threads per CTA");
+  static_assert(!SETREG || (NCHOL % 4 == 0 && (NPROD + 1) % 4 == 0 && kThreads == 640), "setmaxnreg: warpgroups per role");
+  static_assert(!SETREG || 32 * (kRegsDrain + (NCHOL / 4) * kRegsChol + ((16 - NCHOL) / 4) * kRegsProd) <= 5 * 96 * 32,
                 "register pool");
+  static_assert(!kTma || kStages >= (kAhead + 1) * kProdWarps, "ring too shallow for the gather depth");
 };
+// short rows (solve-bound) / long rows (gather-bound); see launch_row_update_v2
+// (development overrides: -DALS_V2_S_NCHOL=.. -DALS_V2_S_NPROD=.. -DALS_V2_S_STAGES=.. -DALS_V2_S_AHEAD=..
+// -DALS_V2_S_SETREG=0|1 for the short-row mix, ALS_V2_L_* for the long-row mix)
+#ifndef ALS_V2_S_NCHOL
+#define ALS_V2_S_NCHOL 8
+#define ALS_V2_S_NPROD 7
+#define ALS_V2_S_STAGES 24
+#define ALS_V2_S_AHEAD 2
+#define ALS_V2_S_SETREG 1
+#endif
+#ifndef ALS_V2_L_NCHOL
+#define ALS_V2_L_NCHOL 4
+#define ALS_V2_L_NPROD 11
+#define ALS_V2_L_STAGES 34
+#define ALS_V2_L_AHEAD 2
+#define ALS_V2_L_SETREG 1
+#endif
+using MixShort = Mix<ALS_V2_S_NCHOL, ALS_V2_S_NPROD, ALS_V2_S_STAGES, ALS_V2_S_AHEAD, ALS_V2_S_SETREG != 0>;
+using MixLong = Mix<ALS_V2_L_NCHOL, ALS_V2_L_NPROD, ALS_V2_L_STAGES, ALS_V2_L_AHEAD, ALS_V2_L_SETREG != 0>;
 
-template <int KS, int NCHOL>
+template <int KS, class MX>
 struct Smem {
   using WP = WPanels<KS>;
-  using MX = Mix<NCHOL>;
+  static constexpr int NCHOL = MX::kCholWarps;
   static constexpr size_t kRing = (size_t)MX::kStages * 4096;
   static constexpr size_t kSlotBytes = sizeof(float) * WP::kFloats;
   static constexpr size_t off_slots = kRing;                                    // [NCHOL] W slots
-  static constexpr size_t off_ng = off_slots + NCHOL * kSlotBytes;              // -G, panel layout
-  static constexpr size_t off_bpart = off_ng + kSlotBytes;                      // [NCHOL][P][KS]
-  static constexpr size_t off_scratch = off_bpart + sizeof(float) * NCHOL * MX::kProdWarps * KS;
+  static constexpr size_t off_ng = off_slots + MX::kWSlots * kSlotBytes;        // -G, panel layout
+  static constexpr size_t off_bpart = off_ng + kSlotBytes;                      // [kBSlots][P][KS]
+  static constexpr size_t off_scratch = off_bpart + sizeof(float) * MX::kBSlots * MX::kProdWarps * KS;
   static constexpr size_t off_bars = off_scratch + sizeof(float) * NCHOL * CholBlocked<KS>::kScratch;
-  static constexpr int kNumBars = 2 * MX::kStages + 2 * kAccSlots + 4 * NCHOL;
+  static constexpr int kNumBars = 3 * MX::kStages + 2 * kAccSlots + 2 * MX::kWSlots + 2 * MX::kBSlots;
   static constexpr size_t off_misc = (off_bars + sizeof(uint64_t) * kNumBars + 15) / 16 * 16;
   static constexpr size_t kTotal = off_misc + 64;
   static_assert(kTotal <= 227 * 1024, "shared memory per CTA");
@@ -120,6 +180,26 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)
 
 __device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+
+// TMA bulk copy global -> shared (one contiguous run of `bytes`, 16-byte aligned both sides), its
+// completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t mbar_saddr) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_saddr), "l"(src), "r"(bytes), "r"(mbar_saddr)
+               : "memory");
+}
+// Ampere-style asynchronous 16-byte copy global -> shared (no register staging); src_bytes = 0
+// zero-fills the destination instead of reading
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst_saddr, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_saddr), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once all earlier cp.async of this thread are done
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
 // Row table of a batch of 32 rows (rows rb, rb + step, ...): one row per lane.
@@ -154,16 +234,16 @@ __device__ __forceinline__ void load_batch(const RowUpdateParams& p, long long r
   B.ne_mask = __ballot_sync(kFull, B.cnt > 0);
 }
 
-template <int KS, int NCHOL>
-__global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpdateParams p) {
+template <int KS, class MX>
+__global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const RowUpdateParams p) {
   static_assert(KS == 64, "second-generation kernel: k = 64");
   using G = umma::StageGeom<KS>;
-  using S = Smem<KS, NCHOL>;
+  using S = Smem<KS, MX>;
   using WP = WPanels<KS>;
   using CB = CholBlocked<KS>;
-  using MX = Mix<NCHOL>;
   constexpr int kCholWarps = MX::kCholWarps, P = MX::kProdWarps, kFirstProd = MX::kFirstProd;
-  constexpr int kStages = MX::kStages;
+  constexpr int kStages = MX::kStages, kWSlots = MX::kWSlots, kBSlots = MX::kBSlots;
+  constexpr int kMmaWarp = MX::kMmaWarp, kThreads = MX::kThreads;
   constexpr int kRegsProd = MX::kRegsProd;
   constexpr int E = G::kEntries;  // 16 entries per stage
   constexpr int kPS = WP::kPS;
@@ -178,28 +258,39 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
   uint64_t* acc_full = empty + kStages;
   uint64_t* acc_empty = acc_full + kAccSlots;
   uint64_t* w_full = acc_empty + kAccSlots;
-  uint64_t* w_empty = w_full + kCholWarps;
-  uint64_t* b_full = w_empty + kCholWarps;
-  uint64_t* b_empty = b_full + kCholWarps;
+  uint64_t* w_empty = w_full + kWSlots;
+  uint64_t* b_full = w_empty + kWSlots;
+  uint64_t* b_empty = b_full + kBSlots;
+  uint64_t* raw_full = b_empty + kBSlots;  // [kStages] gathered bytes of a stage have landed (kTma)
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem + S::off_misc);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int k = p.k;
+#ifdef ALS_PROFILE_WAITS
+  const long long prof_t0 = clock64();
+#endif
   if (tid == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // operand atoms need 1024-byte alignment
 
   if (tid == 0) {
     for (int i = 0; i < kStages; i++) {
       mbar_init(&full[i], 32);  // the 32 lanes of the producer warp that owns the stage
       mbar_init(&empty[i], 1);
+      mbar_init(&raw_full[i], 32);  // copy-completion arrivals of the 32 lanes that gathered the stage
     }
     for (int i = 0; i < kAccSlots; i++) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 128);
     }
-    for (int i = 0; i < kCholWarps; i++) {
+    // W hand-off barriers are per SLOT (row u -> slot u % kWSlots): the drain sees every phase of
+    // a slot's barriers in order, and phase n+1 of w_full cannot complete before the one waiter
+    // of phase n (the Cholesky warp of row n * kWSlots + slot) has released the slot.
+    for (int i = 0; i < kWSlots; i++) {
       mbar_init(&w_full[i], 128);
       mbar_init(&w_empty[i], 1);
+    }
+    // rhs hand-off barriers per rhs slot (row u -> slot u % kBSlots), same argument
+    for (int i = 0; i < kBSlots; i++) {
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
@@ -221,8 +312,158 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
   const long long row_step = gridDim.x;
 
   if (warp >= kFirstProd) {
-   if constexpr (kRegsProd < 96) umma::reg_dealloc<kRegsProd>();
+   if constexpr (MX::kSetReg && kRegsProd < 96) umma::reg_dealloc<kRegsProd>();
    if (warp < kMmaWarp) {
+    if constexpr (kTma) {
+    // =========================== producers: async gather + in-place conversion ========
+    // Each producer owns every P-th stage.  For a stage it (1) issues the asynchronous gather
+    // of the stage kAhead own-stages ahead (16-byte cp.async copies straight into that stage's
+    // ring slot, zero-fill beyond the row's last entry, completion on the slot's mbarrier),
+    // (2) prefetches the indices / values of the stage after that, (3) waits for its current
+    // stage's bytes, reads the raw fp32 rows from the slot and converts them in place.
+    const int pw = warp - kFirstProd;
+    const int q = lane & 15;    // 16-byte chunk of the factor row / entry whose scalars this lane holds
+    const int sub = lane >> 4;  // which of the two entries of a pass
+    constexpr int D = MX::kAhead;
+    uint32_t oh0, ol0;
+    G::slots(sub, q, oh0, ol0);  // pass 0; lo = hi ^ 32
+    const uint32_t ring_a = smem_u32(ring);
+    uint32_t f = (uint32_t)pw;              // my current stage
+    uint32_t slot = (uint32_t)pw, par = 0;  // its ring slot and phase parity
+    uint32_t base = 0;
+    int useq_base = 0;
+    float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float alpha = p.alpha;
+    const bool recon = p.reconstruct_r != 0;
+    for (long long rb = blockIdx.x; rb < p.n_rows; rb += 32 * row_step) {
+      RowBatch B;
+      load_batch<E>(p, rb, row_step, lane, base, B);
+      // index / value of entry q of flat stage ff (-1 / 0 beyond the stage or the batch)
+      auto fetch = [&](uint32_t ff, int& idx_o, float& val_o) {
+        idx_o = -1;
+        val_o = 0.f;
+        if (ff < B.batch_end) {  // warp-uniform
+          const int i = __ffs(__ballot_sync(kFull, B.end > ff)) - 1;
+          const int cnt = __shfl_sync(kFull, B.cnt, i);
+          const uint32_t end = __shfl_sync(kFull, B.end, i);
+          const long long e0 = shfl_i64(B.e0, i);
+          const int st = (int)(ff - (end - (uint32_t)((cnt + E - 1) / E)));
+          if (st * E + q < cnt) {
+            idx_o = ld_stream_i32(p.col_idx + e0 + st * E + q);
+            val_o = ld_stream_f32(p.val + e0 + st * E + q);
+          }
+        }
+      };
+      // gather of one stage into ring slot gs (phase parity gp): every lane copies chunk q of
+      // entries sub, sub + 2, ...; the slot's mbarrier gets this lane's arrival when they land
+      auto issue = [&](int my_idx, uint32_t gs, uint32_t gp) {
+        mbar_wait_id(&empty[gs], gp ^ 1u, 1);  // the MMA has read the slot's previous stage
+        const uint32_t dst = ring_a + gs * (uint32_t)G::kBytes + (uint32_t)(sub * (KS * 4) + q * 16);
+#pragma unroll
+        for (int ps = 0; ps < 8; ps++) {
+          const int ci = __shfl_sync(kFull, my_idx, sub + 2 * ps);
+          cp_async_16_zfill(dst + (uint32_t)(2 * ps * (KS * 4)),
+                            p.M + (long long)(ci < 0 ? 0 : ci) * KS + 4 * q, ci < 0 ? 0u : 16u);
+        }
+        cp_async_mbar_arrive_noinc(&raw_full[gs]);
+      };
+      // queue of my next D + 1 stages' (index, value): position d <-> stage f + d * P; shifted
+      // down by one every step (a few register moves instead of D + 1 unrolled loop bodies)
+      int q_idx[D + 1];
+      float q_val[D + 1];
+#pragma unroll
+      for (int d = 0; d <= D; d++) fetch(f + (uint32_t)(d * P), q_idx[d], q_val[d]);
+      uint32_t gslot = slot, gpar = par;  // ring position of the next stage to gather
+#pragma unroll
+      for (int d = 0; d < D; d++) {
+        if (f + (uint32_t)(d * P) < B.batch_end) issue(q_idx[d], gslot, gpar);
+        gslot += P;
+        if (gslot >= (uint32_t)kStages) { gslot -= kStages; gpar ^= 1u; }
+      }
+#pragma unroll 1
+      while (f < B.batch_end) {
+        {
+          const float my_val = q_val[0];
+          // (1) gather of the stage D own-stages ahead
+          if (f + (uint32_t)(D * P) < B.batch_end) issue(q_idx[D], gslot, gpar);
+          gslot += P;
+          if (gslot >= (uint32_t)kStages) { gslot -= kStages; gpar ^= 1u; }
+          // (2) shift the queue; indices / values of the stage after that into its last position
+#pragma unroll
+          for (int d = 0; d < D; d++) { q_idx[d] = q_idx[d + 1]; q_val[d] = q_val[d + 1]; }
+          fetch(f + (uint32_t)((D + 1) * P), q_idx[D], q_val[D]);
+          // (3) my current stage
+          const int i = __ffs(__ballot_sync(kFull, B.end > f)) - 1;
+          const int cnt = __shfl_sync(kFull, B.cnt, i);
+          const uint32_t end = __shfl_sync(kFull, B.end, i);
+          const int nst = (cnt + E - 1) / E;
+          const int st = (int)(f - (end - (uint32_t)nst));
+          // per-entry scalars, once per entry (lane q of either half):
+          // SYRK weight (c_u - 1) = alpha*|r| (ALS.java:471-479), 0 when reconstructing R (:466-469);
+          // rhs weight r (:466-469) or c_u gated on r > 0 (:480-482)
+          const float ar = alpha * fabsf(my_val);
+          const float my_s = recon ? 0.f : sqrt_approx(ar);
+          const float my_cb = recon ? my_val : (my_val > 0.f ? 1.f + ar : 0.f);
+          mbar_wait_id(&raw_full[slot], par, 11);
+          const unsigned char* raw = ring + (size_t)slot * G::kBytes;
+          float4 y[8];
+#pragma unroll
+          for (int ps = 0; ps < 8; ps++)  // (zero-filled beyond the stage's entries)
+            y[ps] = *reinterpret_cast<const float4*>(raw + (sub + 2 * ps) * (KS * 4) + q * 16);
+          __syncwarp();  // every lane holds its part of the raw rows: the tile may be overwritten
+          const uint32_t st_hi = ring_a + slot * (uint32_t)G::kBytes + oh0;  // shared-window address
+#pragma unroll
+          for (int ps = 0; ps < 8; ps++) {
+            const float sc = __shfl_sync(kFull, my_s, sub + 2 * ps);
+            const float cb = __shfl_sync(kFull, my_cb, sub + 2 * ps);
+            const float4 v = make_float4(y[ps].x * sc, y[ps].y * sc, y[ps].z * sc, y[ps].w * sc);
+            // bf16 hi + bf16 lo, round-to-nearest both times
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y);
+            const __nv_bfloat162 h23 = __floats2bfloat162_rn(v.z, v.w);
+            const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01);
+            const uint32_t u23 = *reinterpret_cast<const uint32_t*>(&h23);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __uint_as_float(u01 << 16),
+                                                             v.y - __uint_as_float(u01 & 0xffff0000u));
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __uint_as_float(u23 << 16),
+                                                             v.w - __uint_as_float(u23 & 0xffff0000u));
+            // pass ps fills K-row 2(ps&3)+sub of K-atom ps>>2: relative to pass 0 the slot address
+            // differs by ^((ps&3) << 5) (the swizzle), ^((ps&3) << 8) (the K-row; both below the
+            // ring's 1 KB alignment, so XOR on the address is exact) and + (ps>>2) * 2048
+            const uint32_t xo = (uint32_t)(((ps & 3) << 5) | ((ps & 3) << 8));
+            const uint32_t ko = (uint32_t)((ps >> 2) << 11);
+            sts_v2((st_hi ^ xo) + ko, u01, u23);
+            sts_v2((st_hi ^ (xo ^ 32u)) + ko, *reinterpret_cast<const uint32_t*>(&l01),
+                   *reinterpret_cast<const uint32_t*>(&l23));
+            bacc.x = fmaf(cb, y[ps].x, bacc.x);
+            bacc.y = fmaf(cb, y[ps].y, bacc.y);
+            bacc.z = fmaf(cb, y[ps].z, bacc.z);
+            bacc.w = fmaf(cb, y[ps].w, bacc.w);
+          }
+          // my last stage of this row: publish the partial rhs of my stages (before the stage's
+          // `full` arrive: the MMA warp's "rhs complete" signal then covers it)
+          if (st + P >= nst) {
+            const int useq = useq_base + __popc(B.ne_mask & ((1u << i) - 1u));
+            const int bslot = useq % kBSlots;
+            float4 v = bacc;
+            v.x += __shfl_xor_sync(kFull, v.x, 16);
+            v.y += __shfl_xor_sync(kFull, v.y, 16);
+            v.z += __shfl_xor_sync(kFull, v.z, 16);
+            v.w += __shfl_xor_sync(kFull, v.w, 16);
+            mbar_wait_id(&b_empty[bslot], (uint32_t)(((useq / kBSlots) & 1) ^ 1), 0);
+            if (lane < 16) *reinterpret_cast<float4*>(bpart + (bslot * P + pw) * KS + 4 * q) = v;
+            bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&full[slot]);
+          f += P;
+          slot += P;
+          if (slot >= (uint32_t)kStages) { slot -= kStages; par ^= 1u; }
+        }
+      }
+      base = B.batch_end;
+      useq_base += __popc(B.ne_mask);
+    }
+    } else {
     // =========================== producers ===========================================
     const int pw = warp - kFirstProd;
     const int q = lane & 15;    // 16-byte chunk of the factor row / entry slot this lane prepares
@@ -326,13 +567,13 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
         // `full` arrive: the MMA warp's "rhs complete" signal then covers it)
         if (st + P >= (cnt + E - 1) / E) {
           const int useq = useq_base + __popc(B.ne_mask & ((1u << i) - 1u));
-          const int bslot = useq % kCholWarps;
+          const int bslot = useq % kBSlots;
           float4 v = bacc;
           v.x += __shfl_xor_sync(kFull, v.x, 16);
           v.y += __shfl_xor_sync(kFull, v.y, 16);
           v.z += __shfl_xor_sync(kFull, v.z, 16);
           v.w += __shfl_xor_sync(kFull, v.w, 16);
-          mbar_wait_id(&b_empty[bslot], (uint32_t)(((useq / kCholWarps) & 1) ^ 1), 0);
+          mbar_wait_id(&b_empty[bslot], (uint32_t)(((useq / kBSlots) & 1) ^ 1), 0);
           if (lane < 16) *reinterpret_cast<float4*>(bpart + (bslot * P + pw) * KS + 4 * q) = v;
           bacc = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -344,6 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
       }
       base = B.batch_end;
       useq_base += __popc(B.ne_mask);
+    }
     }
    } else {
     // =========================== MMA issuer ==========================================
@@ -371,7 +613,15 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
         mbar_wait_id(&acc_empty[a], ((gseg / kAccSlots) & 1) ^ 1, 2);
         const uint32_t d_tmem = tmem_base + a * (uint32_t)G::kN;
         for (int t = 0; t < n; t++) {
+#ifdef ALS_PROFILE_WAITS
+          {
+            const long long t0 = clock64();
+            mbar_wait_addr(full_a, par);
+            if (lane == 0) atomicAdd(&umma::g_wait_cycles[3], (unsigned long long)(clock64() - t0));
+          }
+#else
           mbar_wait_addr(full_a, par);
+#endif
           tc_fence_after_sync();
           umma::mma_bf16_ss_same_elect(d_tmem, dlo, dhi, idesc, (t > 0) ? 1u : 0u);
           umma::mma_commit_addr_elect(empty_a);  // frees the operand stage once the MMA has read it
@@ -384,7 +634,7 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
         umma::mma_commit_elect(&acc_full[a]);  // accumulator segment complete
       }
       // every stage of the row has been seen full: the producers' rhs partials are in place
-      if (lane == 0) mbar_arrive(&b_full[useq % kCholWarps]);
+      if (lane == 0) mbar_arrive(&b_full[useq % kBSlots]);
       __syncwarp();
       useq++;
     }
@@ -394,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
     // Warp qd owns TMEM lane quarter qd = matrix rows 16qd..16qd+15 (lanes +0..15: hi operand
     // rows, +16..31: lo rows); D's column group fc (32 columns) = [hi | lo] of features
     // 16fc..16fc+15.  Block (qd, fc), fc <= qd, of W = the sum of the four hi/lo quadrants.
-    umma::reg_dealloc<kRegsDrain>();
+    if constexpr (MX::kSetReg) umma::reg_dealloc<kRegsDrain>();
     const int qd = warp;
     const int g = lane >> 2, t = lane & 3;
     const uint32_t lane_hi = (uint32_t)(32 * qd) << 16, lane_lo = (uint32_t)(32 * qd + 16) << 16;
@@ -415,14 +665,14 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
         if (cnt == 0) continue;
         const int nst = (cnt + E - 1) / E;
         const int nseg = (nst + kSegStages - 1) / kSegStages;
-        const int ws = useq % kCholWarps;
+        const int ws = useq % kWSlots;
         float* slot = slots + ws * WP::kFloats;
         // W = G + lambda*alpha*n_u*I + ... (ALS.java:447-450, 488-492); padding rows (>= k) get a
         // unit diagonal so the factorisation stays finite.  Rows g and g+8 of the block:
         const float lam_n = (float)(p.lambda_alpha * (double)cnt);
         const float lam0 = (16 * qd + g < k) ? lam_n : 1.f;
         const float lam1 = (16 * qd + g + 8 < k) ? lam_n : 1.f;
-        mbar_wait_id(&w_empty[ws], (uint32_t)(((useq / kCholWarps) & 1) ^ 1), 4);
+        mbar_wait_id(&w_empty[ws], (uint32_t)(((useq / kWSlots) & 1) ^ 1), 4);
         for (int seg = 0; seg < nseg; seg++, gseg++) {
           const int a = (int)(gseg % kAccSlots);
           mbar_wait_id(&acc_full[a], (gseg / kAccSlots) & 1, 5);
@@ -471,9 +721,10 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
     }
   } else {
     // =========================== Cholesky warps ======================================
-    if constexpr (kRegsChol > 96) umma::reg_alloc<kRegsChol>();
+    if constexpr (MX::kSetReg && kRegsChol > 96) umma::reg_alloc<kRegsChol>();
     const int cw = warp - kFirstChol;
-    float* slot = slots + cw * WP::kFloats;
+    constexpr int kGroups = (ALS_V2_LOCKSTEP > kCholWarps / 2) ? kCholWarps / 2 : ALS_V2_LOCKSTEP;
+    constexpr int kGroupWarps = kGroups ? kCholWarps / kGroups : 1;
     float* scratch = reinterpret_cast<float*>(smem + S::off_scratch) + cw * CB::kScratch;
     int useq = 0;
     uint32_t base = 0;
@@ -491,8 +742,8 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
         const long long row = rb + ib * row_step;
         const int nst = (cnt + E - 1) / E;
         const int smod = __shfl_sync(kFull, smod_l, ib);
-        const uint32_t ph = (uint32_t)((useq / kCholWarps) & 1);
-        mbar_wait_id(&b_full[cw], ph, 7);
+        const int bs = useq % kBSlots;
+        mbar_wait_id(&b_full[bs], (uint32_t)((useq / kBSlots) & 1), 7);
         float b[CB::kS];
 #pragma unroll
         for (int s = 0; s < CB::kS; s++) b[s] = 0.f;
@@ -501,15 +752,24 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
           int rel = w - smod;
           if (rel < 0) rel += P;
           if (rel < nst) {  // producer w had a stage in this row
-            const float* bp = bpart + (cw * P + w) * KS;
+            const float* bp = bpart + (bs * P + w) * KS;
 #pragma unroll
             for (int s = 0; s < CB::kS; s++) b[s] += bp[lane + 32 * s];
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&b_empty[cw]);
-        mbar_wait_id(&w_full[cw], ph, 6);
-        if (ALS_V2_LOCKSTEP) bar_sync(1, kCholWarps * 32);
+        if (lane == 0) mbar_arrive(&b_empty[bs]);
+        const int ws = useq % kWSlots;
+        float* slot = slots + ws * WP::kFloats;
+        mbar_wait_id(&w_full[ws], (uint32_t)((useq / kWSlots) & 1), 6);
+#ifdef ALS_PROFILE_WAITS
+        const long long tb = clock64();
+        if (kGroups) bar_sync(1 + cw / kGroupWarps, kGroupWarps * 32);
+        const long long ts = clock64();
+        if (lane == 0) atomicAdd(&umma::g_wait_cycles[9], (unsigned long long)(ts - tb));
+#else
+        if (kGroups) bar_sync(1 + cw / kGroupWarps, kGroupWarps * 32);
+#endif
 #ifdef ALS_DEBUG_SLOT
         // development builds only (scripts/v2_debug.py): copy the slot (N = -W_u) and the rhs of
         // one row out before the solve touches them
@@ -522,14 +782,20 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
 #endif
         const float dmax = CB::diag_max(slot, lane, k);
         const bool ok = CB::factor_solve(slot, scratch, b, dmax, p.threshold, kCondLimit, lane, k);
+#ifdef ALS_PROFILE_WAITS
+        if (lane == 0) atomicAdd(&umma::g_wait_cycles[10], (unsigned long long)(clock64() - ts));
+#endif
         __syncwarp();
-        if (lane == 0) mbar_arrive(&w_empty[cw]);
+        if (lane == 0) mbar_arrive(&w_empty[ws]);
         if (ok) {
           float* dst = p.out + (p.row_offset + row) * KS;
 #pragma unroll
           for (int s = 0; s < CB::kS; s++) {
             const int r = lane + 32 * s;
-            if (r < k) dst[r] = b[s];
+            if (r < k) {
+              dst[r] = b[s];
+              push_to_peers(p, (p.row_offset + row) * KS + r, b[s]);
+            }
           }
         } else if (lane == 0) {
           const int rs = atomicAdd(p.retry_count, 1);
@@ -539,25 +805,28 @@ __global__ void __launch_bounds__(kThreads, 1) row_update_v2_kernel(const RowUpd
       }
       base = B.batch_end;
     }
-    // tail: warps without a row in the last round still meet the others at the barrier
-    if (ALS_V2_LOCKSTEP && (useq % kCholWarps) != 0 && cw >= (useq % kCholWarps))
-      bar_sync(1, kCholWarps * 32);
+    // tail: warps without a row in the last round still meet their group at the barrier
+    if (kGroups && (useq % kCholWarps) != 0 && cw >= (useq % kCholWarps))
+      bar_sync(1 + cw / kGroupWarps, kGroupWarps * 32);
   }
 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == kMmaWarp) umma::tmem_dealloc(tmem_base, kTmemCols);
+#ifdef ALS_PROFILE_WAITS
+  if (tid == 0) atomicAdd(&umma::g_wait_cycles[8], (unsigned long long)(clock64() - prof_t0));
+#endif
 }
 
 }  // namespace v2
 
-template <int KS, int NCHOL>
+template <int KS, class MX>
 inline int launch_row_update_v2_t(const RowUpdateParams& p, int sm_count, cudaStream_t stream, char* err,
                                   size_t err_len) {
-  using S = v2::Smem<KS, NCHOL>;
+  using S = v2::Smem<KS, MX>;
   long long grid = sm_count;
   if (grid > p.n_rows) grid = p.n_rows > 0 ? p.n_rows : 1;
-  v2::row_update_v2_kernel<KS, NCHOL><<<(int)grid, v2::kThreads, S::kTotal, stream>>>(p);
+  v2::row_update_v2_kernel<KS, MX><<<(int)grid, MX::kThreads, S::kTotal, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, err_len, "row_update_v2 launch: %s", cudaGetErrorString(e));

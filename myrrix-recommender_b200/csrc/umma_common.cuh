@@ -58,6 +58,19 @@ __device__ __forceinline__ void mbar_wait_id(uint64_t* bar, uint32_t parity, int
   const long long dt = clock64() - t0;
   if ((threadIdx.x & 31) == 0) atomicAdd(&g_wait_cycles[id], (unsigned long long)dt);
 }
+#elif defined(ALS_WATCHDOG)
+// development builds: a wait that lasts longer than ~2 s reports who is stuck on what and traps
+__device__ __forceinline__ void mbar_wait_id(uint64_t* bar, uint32_t parity, int id) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      if ((threadIdx.x & 31) == 0)
+        printf("WATCHDOG cta %d warp %d wait id %d bar +%u parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), id,
+               (unsigned)(smem_u32(bar)), parity);
+      __trap();
+    }
+  }
+}
 #else
 __device__ __forceinline__ void mbar_wait_id(uint64_t* bar, uint32_t parity, int) {
   mbar_wait(bar, parity);

@@ -54,7 +54,15 @@ def main():
         ok = C.c_int(0)
         rc = fn(W.ctypes.data_as(fp), b.ctypes.data_as(fp), k, 1e-5, x.ctypes.data_as(fp), C.byref(ok))
         ref = np.linalg.solve(W.astype(np.float64), b.astype(np.float64))
-        print("  k=%d rc=%d ok=%d err=%.2e" % (k, rc, ok.value, rel_err(x, ref)[0]))
+        rc = fn(W.ctypes.data_as(fp), b.ctypes.data_as(fp), k, 1e-5, x.ctypes.data_as(fp), C.byref(ok))  # warm I-cache
+        print("  k=%d rc=%d ok=%d err=%.2e  cycles (idle SM, 2nd run) %d" % (
+            k, rc, ok.value, rel_err(x, ref)[0], lib.als_debug_last_solve_cycles()))
+        if hasattr(lib, "als_debug_solve_prof"):
+            buf = (C.c_longlong * 8)()
+            lib.als_debug_solve_prof(buf)  # two solves since the last read
+            names = ["panel load", "16 column steps", "write-back + fragments", "trailing HMMA blocks",
+                     "backward: rows below + butterfly", "backward: in-block solve"]
+            print("     per solve:", ", ".join("%s %d" % (n, buf[i] // 2) for i, n in enumerate(names)))
         if rel_err(x, ref)[0] > 1e-4 and k == 64:
             # which entries are wrong?
             bad = np.nonzero(np.abs(x - ref) > 1e-3 * np.abs(ref).max())[0]

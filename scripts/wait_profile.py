@@ -21,8 +21,9 @@ U, I, nnz, k = cfgs[name]
 L = M._native.load()
 L.als_debug_wait_cycles.argtypes = [C.POINTER(C.c_uint64)]
 names = ["prod:b_empty", "prod:empty", "mma:acc_empty", "mma:full", "drain:w_empty", "drain:acc_full",
-         "chol:w_full", "chol:b_full", "kernel total (per CTA sum)", "chol:lockstep", "chol:factor_solve"]
-warps = [7, 7, 1, 1, 4, 4, 8, 8, 1, 8, 8]
+         "chol:w_full", "chol:b_full", "kernel total (per CTA sum)", "chol:lockstep", "chol:factor_solve",
+         "prod:raw_full"]
+warps = [7, 7, 1, 1, 4, 4, 8, 8, 1, 8, 8, 7]
 with M.NativeALS(k) as als:
     als.synth_interactions(U, I, nnz, seed=1234567890)
     als.synth_y0(seed=1234567890)
@@ -33,7 +34,9 @@ with M.NativeALS(k) as als:
         fn(); als.sync()
         L.als_debug_wait_cycles(buf)
         tot = buf[8] / 148.0
+        if half == "Y":  # 4 Cholesky + 11 producer warps
+            warps = [11, 11, 1, 1, 4, 4, 4, 4, 1, 4, 4, 11]
         print("%s-half: kernel cycles per CTA %.3e" % (half, tot))
-        for i in (0, 1, 2, 3, 4, 5, 6, 7, 9, 10):
+        for i in (0, 1, 11, 2, 3, 4, 5, 6, 7, 9, 10):
             per_warp = buf[i] / 148.0 / warps[i]
             print("   %-16s blocked %5.1f%% of the kernel (avg per warp)" % (names[i], 100.0 * per_warp / tot))
