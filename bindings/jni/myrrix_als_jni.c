@@ -3,11 +3,12 @@
  * NOT compiled here (no jni.h in this image).  Build on a box with a JDK:
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude \
  *       bindings/jni/myrrix_als_jni.c -o libmyrrix_als_jni.so -L<dir of libmyrrix_als.so> -lmyrrix_als
- * Every function is a 1:1 forward; buffers are direct ByteBuffers so no copy happens here.
+ * Every function is a 1:1 forward; large arrays are native memory passed by address (no copy here).
  */
 #include <jni.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "myrrix_als.h"
 
@@ -38,23 +39,40 @@ JNIEXPORT jlong JNICALL CLS(nCreate)(JNIEnv *env, jclass c, jint features, jdoub
 
 JNIEXPORT void JNICALL CLS(nDestroy)(JNIEnv *env, jclass c, jlong h) { als_destroy(H(h)); }
 
+/* Large arrays live in native memory owned by the Java side (nAlloc / nFree) and are passed by
+ * address: no 2 GiB ByteBuffer limit, no copy in this stub. */
+#define P(T, a) ((T *)(intptr_t)(a))
+
+JNIEXPORT jlong JNICALL CLS(nAlloc)(JNIEnv *env, jclass c, jlong bytes) {
+  return (jlong)(intptr_t)malloc((size_t)bytes);
+}
+JNIEXPORT void JNICALL CLS(nFree)(JNIEnv *env, jclass c, jlong address) { free(P(void, address)); }
+JNIEXPORT jobject JNICALL CLS(nWindow)(JNIEnv *env, jclass c, jlong address, jlong offset, jint length) {
+  return (*env)->NewDirectByteBuffer(env, P(char, address) + offset, (jlong)length);
+}
+
 JNIEXPORT jint JNICALL CLS(nSetInteractions)(JNIEnv *env, jclass c, jlong h, jlong nUsers, jlong nItems,
-                                             jobject rowPtr, jobject colIdx, jobject val) {
-  return als_set_interactions(H(h), nUsers, nItems,
-                              (const int64_t *)(*env)->GetDirectBufferAddress(env, rowPtr),
-                              (const int32_t *)(*env)->GetDirectBufferAddress(env, colIdx),
-                              (const float *)(*env)->GetDirectBufferAddress(env, val));
+                                             jlong rowPtr, jlong colIdx, jlong val) {
+  return als_set_interactions(H(h), nUsers, nItems, P(const int64_t, rowPtr), P(const int32_t, colIdx),
+                              P(const float, val));
 }
 
-JNIEXPORT jint JNICALL CLS(nSetInteractionsByColumn)(JNIEnv *env, jclass c, jlong h, jobject colPtr,
-                                                     jobject rowIdx, jobject val) {
-  return als_set_interactions_by_column(H(h), (const int64_t *)(*env)->GetDirectBufferAddress(env, colPtr),
-                                        (const int32_t *)(*env)->GetDirectBufferAddress(env, rowIdx),
-                                        (const float *)(*env)->GetDirectBufferAddress(env, val));
+JNIEXPORT jint JNICALL CLS(nSetInteractionsByColumn)(JNIEnv *env, jclass c, jlong h, jlong colPtr,
+                                                     jlong rowIdx, jlong val) {
+  return als_set_interactions_by_column(H(h), P(const int64_t, colPtr), P(const int32_t, rowIdx),
+                                        P(const float, val));
 }
 
-JNIEXPORT jint JNICALL CLS(nSetY)(JNIEnv *env, jclass c, jlong h, jobject y) {
-  return als_set_y(H(h), (const float *)(*env)->GetDirectBufferAddress(env, y));
+JNIEXPORT jint JNICALL CLS(nSetPresentEmptyRows)(JNIEnv *env, jclass c, jlong h, jint which, jintArray rows) {
+  jint n = (*env)->GetArrayLength(env, rows);
+  jint *r = (*env)->GetIntArrayElements(env, rows, NULL);
+  int rc = als_set_present_empty_rows(H(h), which, (const int32_t *)r, n);
+  (*env)->ReleaseIntArrayElements(env, rows, r, JNI_ABORT);
+  return rc;
+}
+
+JNIEXPORT jint JNICALL CLS(nSetY)(JNIEnv *env, jclass c, jlong h, jlong y) {
+  return als_set_y(H(h), P(const float, y));
 }
 
 JNIEXPORT jint JNICALL CLS(nHalfX)(JNIEnv *env, jclass c, jlong h) { return als_half_x(H(h)); }
@@ -74,11 +92,11 @@ JNIEXPORT jint JNICALL CLS(nProbe)(JNIEnv *env, jclass c, jlong h, jintArray use
   return rc;
 }
 
-JNIEXPORT jint JNICALL CLS(nGetX)(JNIEnv *env, jclass c, jlong h, jobject out) {
-  return als_get_x(H(h), (float *)(*env)->GetDirectBufferAddress(env, out));
+JNIEXPORT jint JNICALL CLS(nGetX)(JNIEnv *env, jclass c, jlong h, jlong out) {
+  return als_get_x(H(h), P(float, out));
 }
-JNIEXPORT jint JNICALL CLS(nGetY)(JNIEnv *env, jclass c, jlong h, jobject out) {
-  return als_get_y(H(h), (float *)(*env)->GetDirectBufferAddress(env, out));
+JNIEXPORT jint JNICALL CLS(nGetY)(JNIEnv *env, jclass c, jlong h, jlong out) {
+  return als_get_y(H(h), P(float, out));
 }
 JNIEXPORT jstring JNICALL CLS(nLastError)(JNIEnv *env, jclass c, jlong h) {
   return (*env)->NewStringUTF(env, als_last_error(H(h)));

@@ -37,6 +37,10 @@ struct NcclApi {
                             cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
 };
@@ -55,8 +59,13 @@ bool load_nccl() {
   g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(g_nccl.lib, "ncclAllGather");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
+  g_nccl.Send = (decltype(g_nccl.Send))dlsym(g_nccl.lib, "ncclSend");
+  g_nccl.Recv = (decltype(g_nccl.Recv))dlsym(g_nccl.lib, "ncclRecv");
+  g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(g_nccl.lib, "ncclGroupStart");
+  g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(g_nccl.lib, "ncclGroupEnd");
   g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllGather &&
-              g_nccl.AllReduce && g_nccl.GetErrorString;
+              g_nccl.AllReduce && g_nccl.GetErrorString && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart &&
+              g_nccl.GroupEnd;
   return g_nccl.ok;
 }
 }  // namespace
@@ -614,6 +623,145 @@ int build_transpose_from(als_handle* h, const Csr& A, long long col_begin, long 
   return ALS_OK;
 }
 
+// off[r] = first position in the ascending key array with key >= r * block (r = 0 .. world)
+__global__ void block_boundaries_kernel(const int* __restrict__ keys, long long n, long long block, int world,
+                                        long long* __restrict__ off) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > world) return;
+  const long long target = (long long)r * block;
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((long long)keys[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  off[r] = lo;
+}
+__global__ void shift_keys_kernel(int* keys, long long n, int delta) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) keys[e] -= delta;
+}
+
+// Sharded: build this rank's by-item block from every rank's by-user block on the devices.
+// Each rank sorts its entries by item (stable: users stay ascending), which makes the entries
+// bound for one item block a contiguous run; the runs are exchanged with grouped ncclSend /
+// ncclRecv (an all-to-all), and the received runs -- ordered by source rank, i.e. by user range --
+// are merged by one more stable sort on the item.  Collective.
+int build_by_item_distributed(als_handle* h) {
+  const Csr& A = h->by_user;
+  const int W = h->world;
+  const long long ib_rows = block_rows(h->n_items, W);
+  long long ib, ie;
+  local_block(h, h->n_items, &ib, &ie);
+  if (A.nnz >= (1LL << 31)) return fail(h, ALS_E_UNSUPPORTED, "nnz >= 2^31 per device");
+  const size_t n = (size_t)A.nnz;
+  int *k_in = nullptr, *k_out = nullptr, *rk = nullptr, *rk2 = nullptr;
+  unsigned long long *p_in = nullptr, *p_out = nullptr, *rp = nullptr, *rp2 = nullptr;
+  long long *d_off = nullptr, *d_cnt = nullptr;
+  void* tmp = nullptr;
+  size_t n_recv = 0;
+  int rc = ALS_OK;
+  auto cleanup = [&]() {
+    cudaFree(k_in); cudaFree(k_out); cudaFree(p_in); cudaFree(p_out); cudaFree(rk); cudaFree(rk2);
+    cudaFree(rp); cudaFree(rp2); cudaFree(d_off); cudaFree(d_cnt); cudaFree(tmp);
+  };
+#define DT(expr)                                                                                  \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      cleanup();                                                                                  \
+      return fail(h, _e == cudaErrorMemoryAllocation ? ALS_E_OOM : ALS_E_CUDA, "%s: %s", #expr,   \
+                  cudaGetErrorString(_e));                                                        \
+    }                                                                                             \
+  } while (0)
+#define NC(expr)                                                                                  \
+  do {                                                                                            \
+    ncclResult_t _r = (expr);                                                                     \
+    if (_r != ncclSuccess) {                                                                      \
+      cleanup();                                                                                  \
+      return fail(h, ALS_E_NCCL, "%s: %s", #expr, g_nccl.GetErrorString(_r));                     \
+    }                                                                                             \
+  } while (0)
+  DT(cudaMalloc(&k_in, sizeof(int) * (n ? n : 1)));
+  DT(cudaMalloc(&k_out, sizeof(int) * (n ? n : 1)));
+  DT(cudaMalloc(&p_in, sizeof(unsigned long long) * (n ? n : 1)));
+  DT(cudaMalloc(&p_out, sizeof(unsigned long long) * (n ? n : 1)));
+  DT(cudaMalloc(&d_off, sizeof(long long) * (W + 1)));
+  DT(cudaMalloc(&d_cnt, sizeof(long long) * (size_t)W * W));
+  int item_bits = 1;
+  while ((1LL << item_bits) < h->n_items && item_bits < 31) item_bits++;
+  size_t tmp_bytes = 0;
+  if (n) {
+    expand_rows_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(A.ptr, A.rows, A.row_begin, 0, A.idx, A.val, k_in, p_in);
+    DT(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, item_bits, h->stream));
+    DT(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    DT(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, item_bits, h->stream));
+    h->launches += 2;
+  }
+  block_boundaries_kernel<<<1, 64, 0, h->stream>>>(k_out, (long long)n, ib_rows, W, d_off);
+  long long off[17], cnt_all[16 * 16];
+  DT(cudaMemcpyAsync(off, d_off, sizeof(long long) * (W + 1), cudaMemcpyDeviceToHost, h->stream));
+  DT(cudaStreamSynchronize(h->stream));
+  long long mine[16];
+  for (int r = 0; r < W; r++) mine[r] = off[r + 1] - off[r];
+  DT(cudaMemcpyAsync(d_cnt + (size_t)h->rank * W, mine, sizeof(long long) * W, cudaMemcpyHostToDevice, h->stream));
+  NC(g_nccl.AllGather(d_cnt + (size_t)h->rank * W, d_cnt, (size_t)W, ncclInt64, h->comm, h->stream));
+  DT(cudaMemcpyAsync(cnt_all, d_cnt, sizeof(long long) * (size_t)W * W, cudaMemcpyDeviceToHost, h->stream));
+  DT(cudaStreamSynchronize(h->stream));
+  long long roff[17];
+  roff[0] = 0;
+  for (int src = 0; src < W; src++) roff[src + 1] = roff[src] + cnt_all[src * W + h->rank];
+  n_recv = (size_t)roff[W];
+  if (n_recv >= (1ULL << 31)) { cleanup(); return fail(h, ALS_E_UNSUPPORTED, "nnz >= 2^31 per device"); }
+  DT(cudaMalloc(&rk, sizeof(int) * (n_recv ? n_recv : 1)));
+  DT(cudaMalloc(&rp, sizeof(unsigned long long) * (n_recv ? n_recv : 1)));
+  NC(g_nccl.GroupStart());
+  for (int r = 0; r < W; r++) {
+    if (mine[r] > 0) {
+      NC(g_nccl.Send(k_out + off[r], (size_t)mine[r], ncclInt32, r, h->comm, h->stream));
+      NC(g_nccl.Send(p_out + off[r], (size_t)mine[r], ncclUint64, r, h->comm, h->stream));
+    }
+    const long long c = cnt_all[r * W + h->rank];
+    if (c > 0) {
+      NC(g_nccl.Recv(rk + roff[r], (size_t)c, ncclInt32, r, h->comm, h->stream));
+      NC(g_nccl.Recv(rp + roff[r], (size_t)c, ncclUint64, r, h->comm, h->stream));
+    }
+  }
+  NC(g_nccl.GroupEnd());
+  h->launches += 1;
+  // merge the runs: keys local to my item block, stable sort, pointers + unpack
+  Csr& T = h->by_item;
+  free_csr(h, &T);
+  T.rows = ie - ib;
+  T.nnz = (long long)n_recv;
+  T.row_begin = ib;
+  if ((rc = dev_alloc(h, &T.ptr, (size_t)T.rows + 1)) != ALS_OK || (rc = dev_alloc(h, &T.idx, n_recv)) != ALS_OK ||
+      (rc = dev_alloc(h, &T.val, n_recv)) != ALS_OK) {
+    cleanup();
+    return rc;
+  }
+  if (n_recv == 0) {
+    DT(cudaMemsetAsync(T.ptr, 0, sizeof(long long) * ((size_t)T.rows + 1), h->stream));
+  } else {
+    DT(cudaMalloc(&rk2, sizeof(int) * n_recv));
+    DT(cudaMalloc(&rp2, sizeof(unsigned long long) * n_recv));
+    shift_keys_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(rk, (long long)n_recv, (int)ib);
+    int bits = 1;
+    while ((1LL << bits) < T.rows && bits < 31) bits++;
+    size_t tb2 = 0;
+    DT(cub::DeviceRadixSort::SortPairs(nullptr, tb2, rk, rk2, rp, rp2, (int)n_recv, 0, bits, h->stream));
+    if (tb2 > tmp_bytes) { cudaFree(tmp); tmp = nullptr; DT(cudaMalloc(&tmp, tb2)); tmp_bytes = tb2; }
+    DT(cub::DeviceRadixSort::SortPairs(tmp, tb2, rk, rk2, rp, rp2, (int)n_recv, 0, bits, h->stream));
+    build_ptr_unpack_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(rk2, rp2, T.nnz, T.rows, T.ptr, T.idx, T.val);
+    h->launches += 3;
+  }
+  DT(cudaStreamSynchronize(h->stream));
+  cleanup();
+#undef DT
+#undef NC
+  h->have_by_item = true;
+  return ALS_OK;
+}
+
 int build_transpose(als_handle* h) {
   int rc = build_transpose_from(h, h->by_user, 0, h->n_items, &h->by_item);
   if (rc == ALS_OK) h->have_by_item = true;
@@ -873,8 +1021,11 @@ int als_set_interactions(als_handle* h, int64_t n_users, int64_t n_items, const 
     return rc;
   }
   if (h->world == 1) return build_transpose(h);
+  // sharded with a communicator: the by-item blocks are built from the by-user blocks on the
+  // devices (collective; a later als_set_interactions_by_column overrides it)
+  if (h->comm) return build_by_item_distributed(h);
   CU(h, cudaStreamSynchronize(h->stream));
-  return ALS_OK;  // sharded: caller must follow with als_set_interactions_by_column
+  return ALS_OK;  // partition-only handle: caller must follow with als_set_interactions_by_column
 }
 
 int als_set_interactions_by_column(als_handle* h, const int64_t* col_ptr, const int32_t* row_idx,

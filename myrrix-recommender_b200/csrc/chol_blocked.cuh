@@ -8,9 +8,9 @@
 // raises ALS_E_SINGULAR exactly like the reference.
 //
 // Storage: the drain warps hand over N = -W_u in a "panel-major lower triangle": panel J holds
-// rows 16J .. KS-1 of columns 16J .. 16J+15, row stride kPS floats (80 bytes: 16-byte row loads,
-// ldmatrix rows and the float2 fragment accesses are all (nearly) conflict-free).  The solve
-// runs in place; finished columns hold L (positive), the diagonal holds 1 / L[j][j].
+// rows 16J .. KS-1 of columns 16J .. 16J+15, 64-byte rows whose 16-byte chunks are XOR-swizzled
+// by the row (WPanels::swz: 16-byte row loads, ldmatrix rows and the float2 fragment accesses are
+// all bank-conflict free).  The solve runs in place; finished columns hold L (positive), the diagonal holds 1 / L[j][j].
 //
 // Per panel P (16 columns):
 //   1. panel factorisation on the CUDA cores, rows distributed one (KS = 32) or two (KS = 64)
@@ -42,13 +42,22 @@ namespace als {
 template <int KS>
 struct WPanels {
   static_assert(KS % 16 == 0, "16-column panels");
-  static constexpr int kPS = 20;        // floats per panel row (16 + 4 pad)
+  // floats per panel row: 64 bytes, no padding; the four 16-byte chunks of a row are XOR-swizzled
+  // with swz(row) so that row-per-lane 16-byte accesses, ldmatrix rows and the float2 accumulator
+  // fragments are all bank-conflict free (round 2 profile of the 80-byte padded rows: every
+  // fragment access took twice its wavefronts)
+  static constexpr int kPS = 16;
   static constexpr int kNP = KS / 16;   // panels
   __host__ __device__ static constexpr int panel_off(int J) { return kPS * (J * KS - 8 * J * (J - 1)); }
-  static constexpr int kFloats = kPS * (kNP * KS - 8 * kNP * (kNP - 1));  // KS = 64: 3200 (12.8 KB)
+  static constexpr int kFloats = kPS * (kNP * KS - 8 * kNP * (kNP - 1));  // KS = 64: 2560 (10 KB)
+  // chunk swizzle of local row lr of a panel (depends on bits 1 and 2 of lr only, so rows lr,
+  // lr + 8, lr + 16, ... share it)
+  __host__ __device__ static constexpr int swz(int lr) { return (((lr >> 1) & 1) << 1) | ((lr >> 2) & 1); }
+  // float offset inside a panel of (local row lr, column c in 0..15)
+  __host__ __device__ static constexpr int in_panel(int lr, int c) { return lr * kPS + (c ^ (swz(lr) << 2)); }
   // float offset of element (i, c), i >= 16 * (c / 16)
   __host__ __device__ static constexpr int at(int i, int c) {
-    return panel_off(c >> 4) + (i - (c & ~15)) * kPS + (c & 15);
+    return panel_off(c >> 4) + in_panel(i - (c & ~15), c & 15);
   }
 };
 
@@ -109,7 +118,7 @@ struct CholBlocked {
 #pragma unroll
     for (int s = 0; s < kS; s++) {
       const int row = lane + 32 * s;
-      const float d = -w[WP::panel_off(row >> 4) + (row & 15) * (kPS + 1)];
+      const float d = -w[WP::at(row, row)];
       if (row < k) mine = fmaxf(mine, d);
     }
 #pragma unroll
@@ -134,14 +143,15 @@ struct CholBlocked {
     const bool act0 = lane < nrows;
     const bool act1 = TWO && (lane + 32 < nrows);
     float2 a0[8], a1[8];
+    const int fz = WP::swz(lane);  // chunk swizzle of my rows (lane and lane + 32 share it)
     {
       const float4* s0 = reinterpret_cast<const float4*>(pan + lane * kPS);
       const float4* s1 = reinterpret_cast<const float4*>(pan + (lane + 32) * kPS);
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f), t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (act0) v = s0[q];
-        if (act1) t = s1[q];
+        if (act0) v = s0[q ^ fz];
+        if (act1) t = s1[q ^ fz];
         a0[2 * q] = make_float2(v.x, v.y);
         a0[2 * q + 1] = make_float2(v.z, v.w);
         a1[2 * q] = make_float2(t.x, t.y);
@@ -211,8 +221,8 @@ struct CholBlocked {
       float4* d1 = reinterpret_cast<float4*>(pan + (lane + 32) * kPS);
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        if (act0) d0[q] = make_float4(a0[2 * q].x, a0[2 * q].y, a0[2 * q + 1].x, a0[2 * q + 1].y);
-        if (act1) d1[q] = make_float4(a1[2 * q].x, a1[2 * q].y, a1[2 * q + 1].x, a1[2 * q + 1].y);
+        if (act0) d0[q ^ fz] = make_float4(a0[2 * q].x, a0[2 * q].y, a0[2 * q + 1].x, a0[2 * q + 1].y);
+        if (act1) d1[q ^ fz] = make_float4(a1[2 * q].x, a1[2 * q].y, a1[2 * q + 1].x, a1[2 * q + 1].y);
       }
       if (act0) zx[c0 + lane] = b0;
       if (act1) zx[c0 + lane + 32] = b1;
@@ -228,12 +238,14 @@ struct CholBlocked {
   }
 
   // hi/lo tf32 split of one 16-row block of the panel (two k-steps of 8 columns)
-  __device__ static __forceinline__ void load_frags(const float* blk_rows, int ldm_off, uint32_t (&hi)[2][4],
-                                                    uint32_t (&lo)[2][4]) {
+  // ldmatrix: lane i addresses row r = (i&7) + 8*((i>>3)&1) of the 16-row block and the 16-byte
+  // chunk 2 ks + (i>>4) of the row; ldm_row = r * kPS, ldm_chunk = (i>>4) ^ swz(r)
+  __device__ static __forceinline__ void load_frags(const float* blk_rows, int ldm_row, int ldm_chunk,
+                                                    uint32_t (&hi)[2][4], uint32_t (&lo)[2][4]) {
 #pragma unroll
     for (int ks = 0; ks < 2; ks++) {
       uint32_t raw[4];
-      ldmatrix_x4(smem_addr(blk_rows + 8 * ks + ldm_off), raw);
+      ldmatrix_x4(smem_addr(blk_rows + ldm_row + ((ldm_chunk ^ (2 * ks)) << 2)), raw);
 #pragma unroll
       for (int e = 0; e < 4; e++) {
         hi[ks][e] = raw[e] & 0xffffe000u;
@@ -253,10 +265,11 @@ struct CholBlocked {
     float* ubuf = scratch;
     float* zx = scratch + 32;  // rhs -> z = L^-1 b -> x, by matrix row
     const int g = lane >> 2, t = lane & 3;
-    // ldmatrix: lane i addresses row (i&7) + 8*((i>>3)&1) of a 16-row block, 16-byte column
-    // group (i>>4) of an 8-float k-step
-    const int ldm_off = ((lane & 7) + 8 * ((lane >> 3) & 1)) * kPS + 4 * (lane >> 4);
-    const int cfr_off = g * kPS + 2 * t;  // accumulator fragment: rows g / g+8, columns 2t, 2t+1 (+8)
+    const int ldm_r = (lane & 7) + 8 * ((lane >> 3) & 1);
+    const int ldm_row = ldm_r * kPS, ldm_chunk = (lane >> 4) ^ WP::swz(ldm_r);
+    // accumulator fragment of n-tile nt: rows g / g+8 (same swizzle), columns 8 nt + 2t, +1:
+    // chunk (2 nt + (t>>1)) ^ swz(g), float (t&1)*2 inside it
+    const int cfr_base = g * kPS + (t & 1) * 2, cfr_chunk = (t >> 1) ^ WP::swz(g);
 #pragma unroll
     for (int s = 0; s < kS; s++) zx[lane + 32 * s] = b[s];
     __syncwarp();
@@ -280,7 +293,7 @@ struct CholBlocked {
 #pragma unroll 1
       for (int bj = 0; bj < NB; bj++) {
         uint32_t hiB[2][4], loB[2][4];
-        load_frags(pan + 16 * (bj + 1) * kPS, ldm_off, hiB, loB);
+        load_frags(pan + 16 * (bj + 1) * kPS, ldm_row, ldm_chunk, hiB, loB);
         float* panJ = w + WP::panel_off(P + 1 + bj);
 #pragma unroll
         for (int dd = 0; dd < kNP - 1; dd++) {  // (unrolled: the next block's loads overlap this block's HMMAs)
@@ -293,14 +306,14 @@ struct CholBlocked {
 #pragma unroll
               for (int e = 0; e < 4; e++) { hiA[ks][e] = hiB[ks][e]; loA[ks][e] = loB[ks][e]; }
           } else {
-            load_frags(pan + 16 * (bi + 1) * kPS, ldm_off, hiA, loA);
+            load_frags(pan + 16 * (bi + 1) * kPS, ldm_row, ldm_chunk, hiA, loA);
           }
-          float* blk = panJ + 16 * (bi - bj) * kPS + cfr_off;
+          float* blk = panJ + 16 * (bi - bj) * kPS + cfr_base;
           float chh[2][4], chl[2][4], clh[2][4];
 #pragma unroll
           for (int nt = 0; nt < 2; nt++) {
-            const float2 v0 = *reinterpret_cast<const float2*>(blk + 8 * nt);
-            const float2 v1 = *reinterpret_cast<const float2*>(blk + 8 * kPS + 8 * nt);
+            const float2 v0 = *reinterpret_cast<const float2*>(blk + ((cfr_chunk ^ (2 * nt)) << 2));
+            const float2 v1 = *reinterpret_cast<const float2*>(blk + 8 * kPS + ((cfr_chunk ^ (2 * nt)) << 2));
             chh[nt][0] = v0.x; chh[nt][1] = v0.y; chh[nt][2] = v1.x; chh[nt][3] = v1.y;
 #pragma unroll
             for (int e = 0; e < 4; e++) { chl[nt][e] = 0.f; clh[nt][e] = 0.f; }
@@ -317,9 +330,9 @@ struct CholBlocked {
           }
 #pragma unroll
           for (int nt = 0; nt < 2; nt++) {
-            *reinterpret_cast<float2*>(blk + 8 * nt) =
+            *reinterpret_cast<float2*>(blk + ((cfr_chunk ^ (2 * nt)) << 2)) =
                 make_float2(chh[nt][0] + (chl[nt][0] + clh[nt][0]), chh[nt][1] + (chl[nt][1] + clh[nt][1]));
-            *reinterpret_cast<float2*>(blk + 8 * kPS + 8 * nt) =
+            *reinterpret_cast<float2*>(blk + 8 * kPS + ((cfr_chunk ^ (2 * nt)) << 2)) =
                 make_float2(chh[nt][2] + (chl[nt][2] + clh[nt][2]), chh[nt][3] + (chl[nt][3] + clh[nt][3]));
           }
         }
@@ -347,10 +360,11 @@ struct CholBlocked {
           const float xm = on ? zx[c0 + lr] : 0.f;
           const float2 xx = make_float2(xm, xm);
           const float4* src = reinterpret_cast<const float4*>(pan + lr * kPS);
+          const int fz = WP::swz(lane);
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (on) v = src[q];
+            if (on) v = src[q ^ fz];
             acc[2 * q] = ffma2(make_float2(v.x, v.y), xx, acc[2 * q]);
             acc[2 * q + 1] = ffma2(make_float2(v.z, v.w), xx, acc[2 * q + 1]);
           }
@@ -377,11 +391,11 @@ struct CholBlocked {
       ALS_SP_MARK(4);  // rows below the block + butterfly
       // x_t = dinv_t (z_t - sum_t) - sum_{t' > t} (dinv_t L[t'][t]) x_t': column tt of the diagonal
       // block pre-scaled by 1 / L[tt][tt], so each of the 16 steps is one shuffle + one FMA
-      const float dinv = pan[tt * kPS + tt];
+      const float dinv = pan[WP::in_panel(tt, tt)];
       float v = (zx[c0 + tt] - sum) * dinv;
       float col[16];
 #pragma unroll
-      for (int tp = 1; tp < 16; tp++) col[tp] = pan[tp * kPS + tt] * dinv;
+      for (int tp = 1; tp < 16; tp++) col[tp] = pan[WP::in_panel(tp, tt)] * dinv;
       float xmine = 0.f;
 #pragma unroll
       for (int tp = 15; tp >= 0; tp--) {

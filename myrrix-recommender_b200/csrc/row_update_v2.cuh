@@ -98,8 +98,13 @@ __device__ float g_debug_slot[WPanels<64>::kFloats + 64];
 //   AHEAD   own-stages whose gathers a producer keeps in flight
 //   SETREG  re-balance registers between the roles with setmaxnreg (needs whole warpgroups per
 //           role); otherwise every role lives within the launch register count
-template <int NCHOL, int NPROD, int STAGES, int AHEAD, bool SETREG>
+//   ASYNC   producers gather with asynchronous copies into the ring and convert in place;
+//           otherwise they gather into registers (LDG.128) and store the converted tile once
+//           (fewer shared-memory wavefronts, but the gathers are latency-bound: measured slower on
+//           both halves of the headline workload, 154 vs 143 ms and 68 vs 61 ms)
+template <int NCHOL, int NPROD, int STAGES, int AHEAD, bool SETREG, bool ASYNC>
 struct Mix {
+  static constexpr bool kAsync = ASYNC && kTma;
   static constexpr int kCholWarps = NCHOL;
   static constexpr int kProdWarps = NPROD;
   static constexpr int kFirstProd = kFirstChol + NCHOL;
@@ -108,14 +113,17 @@ struct Mix {
   static constexpr int kStages = STAGES;
   static constexpr int kAhead = AHEAD;
   static constexpr int kWSlots = NCHOL;                 // the solve runs in place: one slot per Cholesky warp
-  static constexpr int kBSlots = NCHOL < 8 ? NCHOL : 8;  // rhs ring (row u -> slot u % kBSlots)
+  // rhs slots, row u -> slot u % kBSlots.  One per Cholesky warp: a slot's consecutive phases are
+  // then waited for by the SAME warp in order (a parity wait by a different warp could run a whole
+  // phase early and pass on the stale parity -- measured: deadlock with 8 slots and 10 warps).
+  static constexpr int kBSlots = NCHOL;
   static constexpr bool kSetReg = SETREG;
   static constexpr int kRegsProd = (kThreads == 640 && NCHOL == 8) ? 80 : 96;
   static_assert(kThreads <= 1024, "threads per CTA");
   static_assert(!SETREG || (NCHOL % 4 == 0 && (NPROD + 1) % 4 == 0 && kThreads == 640), "setmaxnreg: warpgroups per role");
   static_assert(!SETREG || 32 * (kRegsDrain + (NCHOL / 4) * kRegsChol + ((16 - NCHOL) / 4) * kRegsProd) <= 5 * 96 * 32,
                 "register pool");
-  static_assert(!kTma || kStages >= (kAhead + 1) * kProdWarps, "ring too shallow for the gather depth");
+  static_assert(!kAsync || kStages >= (kAhead + 1) * kProdWarps, "ring too shallow for the gather depth");
 };
 // short rows (solve-bound) / long rows (gather-bound); see launch_row_update_v2
 // (development overrides: -DALS_V2_S_NCHOL=.. -DALS_V2_S_NPROD=.. -DALS_V2_S_STAGES=.. -DALS_V2_S_AHEAD=..
@@ -127,6 +135,12 @@ struct Mix {
 #define ALS_V2_S_AHEAD 2
 #define ALS_V2_S_SETREG 1
 #endif
+#ifndef ALS_V2_S_ASYNC
+#define ALS_V2_S_ASYNC 1
+#endif
+#ifndef ALS_V2_L_ASYNC
+#define ALS_V2_L_ASYNC 1
+#endif
 #ifndef ALS_V2_L_NCHOL
 #define ALS_V2_L_NCHOL 4
 #define ALS_V2_L_NPROD 11
@@ -134,8 +148,8 @@ struct Mix {
 #define ALS_V2_L_AHEAD 2
 #define ALS_V2_L_SETREG 1
 #endif
-using MixShort = Mix<ALS_V2_S_NCHOL, ALS_V2_S_NPROD, ALS_V2_S_STAGES, ALS_V2_S_AHEAD, ALS_V2_S_SETREG != 0>;
-using MixLong = Mix<ALS_V2_L_NCHOL, ALS_V2_L_NPROD, ALS_V2_L_STAGES, ALS_V2_L_AHEAD, ALS_V2_L_SETREG != 0>;
+using MixShort = Mix<ALS_V2_S_NCHOL, ALS_V2_S_NPROD, ALS_V2_S_STAGES, ALS_V2_S_AHEAD, ALS_V2_S_SETREG != 0, ALS_V2_S_ASYNC != 0>;
+using MixLong = Mix<ALS_V2_L_NCHOL, ALS_V2_L_NPROD, ALS_V2_L_STAGES, ALS_V2_L_AHEAD, ALS_V2_L_SETREG != 0, ALS_V2_L_ASYNC != 0>;
 
 template <int KS, class MX>
 struct Smem {
@@ -314,7 +328,7 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
   if (warp >= kFirstProd) {
    if constexpr (MX::kSetReg && kRegsProd < 96) umma::reg_dealloc<kRegsProd>();
    if (warp < kMmaWarp) {
-    if constexpr (kTma) {
+    if constexpr (MX::kAsync) {
     // =========================== producers: async gather + in-place conversion ========
     // Each producer owns every P-th stage.  For a stage it (1) issues the asynchronous gather
     // of the stage kAhead own-stages ahead (16-byte cp.async copies straight into that stage's
@@ -649,7 +663,8 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
     const int g = lane >> 2, t = lane & 3;
     const uint32_t lane_hi = (uint32_t)(32 * qd) << 16, lane_lo = (uint32_t)(32 * qd + 16) << 16;
     const bool has_diag = (t == (g >> 1));
-    const int cfr_off = g * kPS + 2 * t;
+    // accumulator-fragment addressing of the swizzled panel rows (see chol_blocked.cuh)
+    const int cfr_base = g * kPS + (t & 1) * 2, cfr_chunk = (t >> 1) ^ WP::swz(g);
     uint32_t gseg = 0;
     int useq = 0;
     for (long long rb = blockIdx.x; rb < p.n_rows; rb += 32 * row_step) {
@@ -692,12 +707,12 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
               wv[e] = (__uint_as_float(r[e]) + __uint_as_float(r[8 + e])) +
                       (__uint_as_float(s[e]) + __uint_as_float(s[8 + e]));
             // wv[4i+0..1]: row g, columns 8i+2t, +1; wv[4i+2..3]: row g+8
-            const int boff = WP::panel_off(fc) + 16 * (qd - fc) * kPS + cfr_off;
+            const int boff = WP::panel_off(fc) + 16 * (qd - fc) * kPS + cfr_base;
             float2 o[4];
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-              const float2 n0 = *reinterpret_cast<const float2*>(src + boff + 8 * i);
-              const float2 n1 = *reinterpret_cast<const float2*>(src + boff + 8 * kPS + 8 * i);
+              const float2 n0 = *reinterpret_cast<const float2*>(src + boff + ((cfr_chunk ^ (2 * i)) << 2));
+              const float2 n1 = *reinterpret_cast<const float2*>(src + boff + 8 * kPS + ((cfr_chunk ^ (2 * i)) << 2));
               o[2 * i] = make_float2(n0.x - wv[4 * i], n0.y - wv[4 * i + 1]);
               o[2 * i + 1] = make_float2(n1.x - wv[4 * i + 2], n1.y - wv[4 * i + 3]);
             }
@@ -708,8 +723,8 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
             }
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-              *reinterpret_cast<float2*>(slot + boff + 8 * i) = o[2 * i];
-              *reinterpret_cast<float2*>(slot + boff + 8 * kPS + 8 * i) = o[2 * i + 1];
+              *reinterpret_cast<float2*>(slot + boff + ((cfr_chunk ^ (2 * i)) << 2)) = o[2 * i];
+              *reinterpret_cast<float2*>(slot + boff + 8 * kPS + ((cfr_chunk ^ (2 * i)) << 2)) = o[2 * i + 1];
             }
           }
           tc_fence_before_sync();

@@ -22,19 +22,25 @@ import myrrix_recommender_b200 as M  # noqa: E402
 from conftest import random_problem, rel_err  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
-PS = 20
+PS = 16
 
 
 def panel_off(J, KS=64):
     return PS * (J * KS - 8 * J * (J - 1))
 
 
+def swz(lr):
+    return (((lr >> 1) & 1) << 1) | ((lr >> 2) & 1)
+
+
 def slot_to_dense(slot, KS=64):
+    """WPanels::at (chol_blocked.cuh): 64-byte panel rows, 16-byte chunks XOR-swizzled by the row."""
     W = np.full((KS, KS), np.nan)
     for c in range(KS):
         J = c // 16
         for i in range(16 * J, KS):
-            W[i, c] = -slot[panel_off(J, KS) + (i - 16 * J) * PS + (c % 16)]
+            lr = i - 16 * J
+            W[i, c] = -slot[panel_off(J, KS) + lr * PS + ((c % 16) ^ (swz(lr) << 2))]
     return W
 
 
@@ -97,16 +103,16 @@ def main():
                   % (mix, rel_err(X, Xo)[0], int(err.argmax()), err.max(), int((err > 1e-4).sum()), retried))
             if not dbg:
                 continue
-            buf = np.zeros(3200 + 64, np.float32)
+            buf = np.zeros(2560 + 64, np.float32)
             lib.als_debug_get_slot.argtypes = [fp, C.c_int]
             lib.als_debug_get_slot(buf.ctypes.data_as(fp), buf.size)
-            Wd = slot_to_dense(buf[:3200])
+            Wd = slot_to_dense(buf[:2560])
             e0, e1 = ptr[r], ptr[r + 1]
             ys = Y0[idx[e0:e1]].astype(np.float64)
             rv = val[e0:e1].astype(np.float64)
             Wn = G + (ys.T * np.abs(rv)) @ ys + 0.1 * (e1 - e0) * np.eye(k)
             bn = (((1 + np.abs(rv)) * (rv > 0))[None, :] @ ys).ravel()
-            print("   row %d: rhs err %.2e" % (r, rel_err(buf[3200:], bn)[0]))
+            print("   row %d: rhs err %.2e" % (r, rel_err(buf[2560:], bn)[0]))
             for bi in range(4):
                 for bj in range(bi + 1):
                     a = Wd[16 * bi:16 * bi + 16, 16 * bj:16 * bj + 16]
