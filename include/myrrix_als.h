@@ -153,6 +153,11 @@ int als_probe(als_handle *h, const int32_t *users, int32_t n_users, const int32_
 int als_get_x(als_handle *h, float *out);
 int als_get_y(als_handle *h, float *out);
 
+/* Rows [first_row, first_row + n_rows) of X (which = 0) or Y (which = 1), n_rows x features fp32,
+ * HOST pointer: a rank of a sharded build reads back just the block it owns.  Call als_sync
+ * first (with a communicator the peers' rows arrive asynchronously). */
+int als_get_factor_block(als_handle *h, int32_t which, int64_t first_row, int64_t n_rows, float *out);
+
 /* Selected rows of X (which = 0) or Y (which = 1): out[i] = factor[rows[i]], n x features fp32,
  * HOST pointers (the per-key lookups of getX().get(id) without copying the whole matrix). */
 int als_get_rows(als_handle *h, int32_t which, const int32_t *rows, int32_t n, float *out);

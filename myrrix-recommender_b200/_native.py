@@ -61,6 +61,7 @@ SYMBOLS = [
     ("als_probe", C.c_int, [_H, _i32p, C.c_int32, _i32p, C.c_int32, _f64p]),
     ("als_get_x", C.c_int, [_H, _f32p]),
     ("als_get_y", C.c_int, [_H, _f32p]),
+    ("als_get_factor_block", C.c_int, [_H, C.c_int32, C.c_int64, C.c_int64, _f32p]),
     ("als_get_rows", C.c_int, [_H, C.c_int32, _i32p, C.c_int32, _f32p]),
     ("als_gramian", C.c_int, [_H, C.c_int32, _f64p]),
     ("als_sync", C.c_int, [_H]),

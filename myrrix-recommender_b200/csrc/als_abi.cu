@@ -1089,6 +1089,20 @@ static int get_factor(als_handle* h, const float* src, long long rows, float* ou
 int als_get_x(als_handle* h, float* out) { return get_factor(h, h ? h->X : nullptr, h ? h->n_users : 0, out); }
 int als_get_y(als_handle* h, float* out) { return get_factor(h, h ? h->Y : nullptr, h ? h->n_items : 0, out); }
 
+int als_get_factor_block(als_handle* h, int32_t which, int64_t first_row, int64_t n_rows, float* out) {
+  if (!h || (which != 0 && which != 1) || first_row < 0 || n_rows < 0 || (n_rows > 0 && !out)) return ALS_E_ARG;
+  const float* F = which == 0 ? h->X : h->Y;
+  const long long limit = which == 0 ? h->n_users : h->n_items;
+  if (!F) return fail(h, ALS_E_STATE, "interactions not set");
+  if (first_row + n_rows > limit) return fail(h, ALS_E_ARG, "row block out of range");
+  if (n_rows == 0) return ALS_OK;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaMemcpy2DAsync(out, sizeof(float) * h->k, F + (size_t)first_row * h->ks, sizeof(float) * h->ks,
+                          sizeof(float) * h->k, (size_t)n_rows, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return ALS_OK;
+}
+
 int als_get_rows(als_handle* h, int32_t which, const int32_t* rows, int32_t n, float* out) {
   if (!h || (which != 0 && which != 1) || n < 0 || (n > 0 && (!rows || !out))) return ALS_E_ARG;
   const float* F = which == 0 ? h->X : h->Y;
