@@ -155,7 +155,7 @@ template <int KS, class MX>
 struct Smem {
   using WP = WPanels<KS>;
   static constexpr int NCHOL = MX::kCholWarps;
-  static constexpr size_t kRing = (size_t)MX::kStages * 4096;
+  static constexpr size_t kRing = (size_t)MX::kStages * 4096 + (KS == 32 ? 2048 : 0);  // +pad: KS = 32 A-operand over-read
   static constexpr size_t kSlotBytes = sizeof(float) * WP::kFloats;
   static constexpr size_t off_slots = kRing;                                    // [NCHOL] W slots
   static constexpr size_t off_ng = off_slots + MX::kWSlots * kSlotBytes;        // -G, panel layout
@@ -212,9 +212,56 @@ __device__ __forceinline__ void cp_async_16_zfill(uint32_t dst_saddr, const void
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// TMA bulk copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_saddr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_saddr), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+
+// Operand stage geometry (one 4 KB ring slot = 256 producer chunks of 16 bytes):
+//   KS = 64: 16 entries, one K-step; two MN-atoms of 64 operand rows (umma::StageGeom<64>).
+//   KS = 32: 32 entries, two K-steps; one MN-atom of 64 operand rows.
+// Operand row of feature f in both: hi at (f/16)*32 + f%16, lo 16 rows further, so TMEM lane
+// quarter q / column group q of D hold the hi and lo parts of features 16q..16q+15 side by side.
+template <int KS>
+struct Geom;
+template <>
+struct Geom<64> : umma::StageGeom<64> {
+  // producer pass ps (entries 2 ps + sub): address relative to pass 0 = ^xo, then +ko
+  __device__ static constexpr uint32_t pass_xor(int ps) { return (uint32_t)(((ps & 3) << 5) | ((ps & 3) << 8)); }
+  __device__ static constexpr uint32_t pass_add(int ps) { return (uint32_t)((ps >> 2) << 11); }
+};
+template <>
+struct Geom<32> {
+  static constexpr int kChunksPerRow = 8;
+  static constexpr int kEntries = 32;
+  static constexpr int kKSteps = 2;
+  static constexpr int kBytes = 4096;
+  static constexpr int kM = 128;  // (rows 64..127 of D are don't-care: the A operand over-reads into the next K-atom)
+  static constexpr int kN = 64;
+  static constexpr uint32_t kLBO = 1024;
+  static constexpr uint32_t kSBO = 1024;
+  static constexpr uint32_t kKStepBytes = 2048;
+  // atom(ks, kb) at ks*2048 + kb*1024; K-row = entry & 7; the 128-byte row is
+  // [hi16 | lo16 | hi16 | lo16] of features 0-15, 16-31
+  __device__ static __forceinline__ void slots(int el, int q, uint32_t& off_hi, uint32_t& off_lo) {
+    const int krow = el & 7, kb = (el >> 3) & 1, ks = (el >> 4) & 1;
+    const int g16 = q >> 2, r = q & 3;
+    const int chunk = 4 * g16 + (r >> 1);
+    const uint32_t row = (uint32_t)ks * 2048u + (uint32_t)kb * 1024u + (uint32_t)krow * 128u;
+    off_hi = row + (uint32_t)((chunk ^ krow) * 16 + (r & 1) * 8);
+    off_lo = off_hi ^ 32u;  // chunk ^ 2
+  }
+  // producer pass ps (entries 4 ps + sub): K-row 4 (ps & 1) + sub of K-atom (ps >> 1) & 1, K-step ps >> 2
+  __device__ static constexpr uint32_t pass_xor(int ps) { return (uint32_t)(((ps & 1) << 6) | ((ps & 1) << 9)); }
+  __device__ static constexpr uint32_t pass_add(int ps) { return (uint32_t)((((ps >> 1) & 1) << 10) + ((ps >> 2) << 11)); }
+};
 
 // Row table of a batch of 32 rows (rows rb, rb + step, ...): one row per lane.
 struct RowBatch {
@@ -250,8 +297,9 @@ __device__ __forceinline__ void load_batch(const RowUpdateParams& p, long long r
 
 template <int KS, class MX>
 __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const RowUpdateParams p) {
-  static_assert(KS == 64, "second-generation kernel: k = 64");
-  using G = umma::StageGeom<KS>;
+  static_assert(KS == 64 || KS == 32, "second-generation kernel: k = 32 or 64");
+  static_assert(KS == 64 || MX::kAsync, "register-gather producers are kept for k = 64 A/B builds only");
+  using G = Geom<KS>;
   using S = Smem<KS, MX>;
   using WP = WPanels<KS>;
   using CB = CholBlocked<KS>;
@@ -336,8 +384,12 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
     // (2) prefetches the indices / values of the stage after that, (3) waits for its current
     // stage's bytes, reads the raw fp32 rows from the slot and converts them in place.
     const int pw = warp - kFirstProd;
-    const int q = lane & 15;    // 16-byte chunk of the factor row / entry whose scalars this lane holds
-    const int sub = lane >> 4;  // which of the two entries of a pass
+    constexpr int CPR = G::kChunksPerRow;  // lanes per factor row (16-byte chunks)
+    constexpr int RPP = 32 / CPR;          // entries per pass of the warp
+    static_assert(E / RPP == 8, "eight passes per stage");
+    const int q = lane % CPR;    // 16-byte chunk of the factor row
+    const int sub = lane / CPR;  // which of the RPP entries of a pass
+    const int el0 = lane % E;    // entry whose index / value / scalars this lane holds
     constexpr int D = MX::kAhead;
     uint32_t oh0, ol0;
     G::slots(sub, q, oh0, ol0);  // pass 0; lo = hi ^ 32
@@ -352,7 +404,7 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
     for (long long rb = blockIdx.x; rb < p.n_rows; rb += 32 * row_step) {
       RowBatch B;
       load_batch<E>(p, rb, row_step, lane, base, B);
-      // index / value of entry q of flat stage ff (-1 / 0 beyond the stage or the batch)
+      // index / value of entry el0 of flat stage ff (-1 / 0 beyond the stage or the batch)
       auto fetch = [&](uint32_t ff, int& idx_o, float& val_o) {
         idx_o = -1;
         val_o = 0.f;
@@ -362,21 +414,21 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
           const uint32_t end = __shfl_sync(kFull, B.end, i);
           const long long e0 = shfl_i64(B.e0, i);
           const int st = (int)(ff - (end - (uint32_t)((cnt + E - 1) / E)));
-          if (st * E + q < cnt) {
-            idx_o = ld_stream_i32(p.col_idx + e0 + st * E + q);
-            val_o = ld_stream_f32(p.val + e0 + st * E + q);
+          if (st * E + el0 < cnt) {
+            idx_o = ld_stream_i32(p.col_idx + e0 + st * E + el0);
+            val_o = ld_stream_f32(p.val + e0 + st * E + el0);
           }
         }
       };
       // gather of one stage into ring slot gs (phase parity gp): every lane copies chunk q of
-      // entries sub, sub + 2, ...; the slot's mbarrier gets this lane's arrival when they land
+      // entries sub, sub + RPP, ...; the slot's mbarrier gets this lane's arrival when they land
       auto issue = [&](int my_idx, uint32_t gs, uint32_t gp) {
         mbar_wait_id(&empty[gs], gp ^ 1u, 1);  // the MMA has read the slot's previous stage
         const uint32_t dst = ring_a + gs * (uint32_t)G::kBytes + (uint32_t)(sub * (KS * 4) + q * 16);
 #pragma unroll
         for (int ps = 0; ps < 8; ps++) {
-          const int ci = __shfl_sync(kFull, my_idx, sub + 2 * ps);
-          cp_async_16_zfill(dst + (uint32_t)(2 * ps * (KS * 4)),
+          const int ci = __shfl_sync(kFull, my_idx, sub + RPP * ps);
+          cp_async_16_zfill(dst + (uint32_t)(RPP * ps * (KS * 4)),
                             p.M + (long long)(ci < 0 ? 0 : ci) * KS + 4 * q, ci < 0 ? 0u : 16u);
         }
         cp_async_mbar_arrive_noinc(&raw_full[gs]);
@@ -423,13 +475,13 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
           float4 y[8];
 #pragma unroll
           for (int ps = 0; ps < 8; ps++)  // (zero-filled beyond the stage's entries)
-            y[ps] = *reinterpret_cast<const float4*>(raw + (sub + 2 * ps) * (KS * 4) + q * 16);
+            y[ps] = *reinterpret_cast<const float4*>(raw + (sub + RPP * ps) * (KS * 4) + q * 16);
           __syncwarp();  // every lane holds its part of the raw rows: the tile may be overwritten
           const uint32_t st_hi = ring_a + slot * (uint32_t)G::kBytes + oh0;  // shared-window address
 #pragma unroll
           for (int ps = 0; ps < 8; ps++) {
-            const float sc = __shfl_sync(kFull, my_s, sub + 2 * ps);
-            const float cb = __shfl_sync(kFull, my_cb, sub + 2 * ps);
+            const float sc = __shfl_sync(kFull, my_s, sub + RPP * ps);
+            const float cb = __shfl_sync(kFull, my_cb, sub + RPP * ps);
             const float4 v = make_float4(y[ps].x * sc, y[ps].y * sc, y[ps].z * sc, y[ps].w * sc);
             // bf16 hi + bf16 lo, round-to-nearest both times
             const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y);
@@ -440,11 +492,10 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
                                                              v.y - __uint_as_float(u01 & 0xffff0000u));
             const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __uint_as_float(u23 << 16),
                                                              v.w - __uint_as_float(u23 & 0xffff0000u));
-            // pass ps fills K-row 2(ps&3)+sub of K-atom ps>>2: relative to pass 0 the slot address
-            // differs by ^((ps&3) << 5) (the swizzle), ^((ps&3) << 8) (the K-row; both below the
-            // ring's 1 KB alignment, so XOR on the address is exact) and + (ps>>2) * 2048
-            const uint32_t xo = (uint32_t)(((ps & 3) << 5) | ((ps & 3) << 8));
-            const uint32_t ko = (uint32_t)((ps >> 2) << 11);
+            // relative to pass 0 the slot address differs by an XOR (swizzle + K-row: below the
+            // ring's 1 KB alignment, so XOR on the address is exact) and an offset (K-atom / K-step)
+            const uint32_t xo = G::pass_xor(ps);
+            const uint32_t ko = G::pass_add(ps);
             sts_v2((st_hi ^ xo) + ko, u01, u23);
             sts_v2((st_hi ^ (xo ^ 32u)) + ko, *reinterpret_cast<const uint32_t*>(&l01),
                    *reinterpret_cast<const uint32_t*>(&l23));
@@ -459,12 +510,15 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
             const int useq = useq_base + __popc(B.ne_mask & ((1u << i) - 1u));
             const int bslot = useq % kBSlots;
             float4 v = bacc;
-            v.x += __shfl_xor_sync(kFull, v.x, 16);
-            v.y += __shfl_xor_sync(kFull, v.y, 16);
-            v.z += __shfl_xor_sync(kFull, v.z, 16);
-            v.w += __shfl_xor_sync(kFull, v.w, 16);
+#pragma unroll
+            for (int off = CPR; off < 32; off <<= 1) {
+              v.x += __shfl_xor_sync(kFull, v.x, off);
+              v.y += __shfl_xor_sync(kFull, v.y, off);
+              v.z += __shfl_xor_sync(kFull, v.z, off);
+              v.w += __shfl_xor_sync(kFull, v.w, off);
+            }
             mbar_wait_id(&b_empty[bslot], (uint32_t)(((useq / kBSlots) & 1) ^ 1), 0);
-            if (lane < 16) *reinterpret_cast<float4*>(bpart + (bslot * P + pw) * KS + 4 * q) = v;
+            if (lane < CPR) *reinterpret_cast<float4*>(bpart + (bslot * P + pw) * KS + 4 * q) = v;
             bacc = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           fence_proxy_async_smem();
@@ -637,7 +691,10 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
           mbar_wait_addr(full_a, par);
 #endif
           tc_fence_after_sync();
-          umma::mma_bf16_ss_same_elect(d_tmem, dlo, dhi, idesc, (t > 0) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < G::kKSteps; ks++)
+            umma::mma_bf16_ss_same_elect(d_tmem, dlo + (uint32_t)(ks * (int)(G::kKStepBytes >> 4)), dhi, idesc,
+                                         (t > 0 || ks > 0) ? 1u : 0u);
           umma::mma_commit_addr_elect(empty_a);  // frees the operand stage once the MMA has read it
           slot++; full_a += 8; empty_a += 8; dlo += (uint32_t)(G::kBytes >> 4);
           if (slot == kStages) {
@@ -695,8 +752,8 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
           const uint32_t tcol = tmem_base + (uint32_t)(a * G::kN);
           const float* src = (seg == 0) ? ng : slot;  // later segments add to what this thread stored
 #pragma unroll
-          for (int fc = 0; fc < 4; fc++) {
-            if (fc > qd) break;  // warp-uniform: block right of the diagonal
+          for (int fc = 0; fc < WP::kNP; fc++) {
+            if (fc > qd || qd >= WP::kNP) break;  // warp-uniform: block right of the diagonal / no such block row
             uint32_t r[16], s[16];
             tmem_ld_16x256b_x4(tcol + lane_hi + 32 * fc, r);
             tmem_ld_16x256b_x4(tcol + lane_lo + 32 * fc, s);
@@ -795,6 +852,8 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
           __syncwarp();
         }
 #endif
+        if (lane == 0) bulk_wait_group_read0();  // the previous row's bulk stores have read the scratch vector
+        __syncwarp();
         const float dmax = CB::diag_max(slot, lane, k);
         const bool ok = CB::factor_solve(slot, scratch, b, dmax, p.threshold, kCondLimit, lane, k);
 #ifdef ALS_PROFILE_WAITS
@@ -803,14 +862,19 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
         __syncwarp();
         if (lane == 0) mbar_arrive(&w_empty[ws]);
         if (ok) {
-          float* dst = p.out + (p.row_offset + row) * KS;
-#pragma unroll
-          for (int s = 0; s < CB::kS; s++) {
-            const int r = lane + 32 * s;
-            if (r < k) {
-              dst[r] = b[s];
-              push_to_peers(p, (p.row_offset + row) * KS + r, b[s]);
-            }
+          // The solution sits in the warp's scratch vector in row order (padding entries 0): one
+          // TMA bulk copy (cp.async.bulk shared -> global, 256 B, warp-uniform addresses) per
+          // destination -- the local factor row and, sharded, the same row of every peer replica
+          // over NVLink -- instead of per-lane stores.
+          float* xs = scratch + 32;
+          const long long eoff = (p.row_offset + row) * KS;
+          fence_proxy_async_smem();  // the solver's generic-proxy writes of xs -> visible to the bulk copy
+          __syncwarp();
+          if (lane == 0) {
+            bulk_s2g(p.out + eoff, smem_u32(xs), KS * 4);
+#pragma unroll 1
+            for (int r = 0; r < p.n_peers; r++) bulk_s2g(p.peer_out[r] + eoff, smem_u32(xs), KS * 4);
+            bulk_commit_group();  // (the scratch vector is reused only after wait_group.read, below)
           }
         } else if (lane == 0) {
           const int rs = atomicAdd(p.retry_count, 1);
@@ -820,6 +884,7 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
       }
       base = B.batch_end;
     }
+    if (lane == 0) bulk_wait_group0();  // every bulk store of this warp has been written
     // tail: warps without a row in the last round still meet their group at the barrier
     if (kGroups && (useq % kCholWarps) != 0 && cw >= (useq % kCholWarps))
       bar_sync(1 + cw / kGroupWarps, kGroupWarps * 32);
