@@ -227,6 +227,35 @@ int als_get_interaction_rows(als_handle *h, int32_t by_column, int64_t first_row
                              int64_t *row_ptr_out, int32_t *idx_out, float *val_out,
                              int64_t capacity);
 
+/* ---- top-N scoring on the resident model ------------------- */
+/* Replaces, for dense indices, ServerRecommender.recommend / recommendToMany
+ * (online/src/net/myrrix/online/ServerRecommender.java:355-441) -> multithreadedTopN (:443-509)
+ * -> RecommendIterator.next (online/.../RecommendIterator.java:68-110) -> TopN
+ * (common/src/net/myrrix/common/TopN.java:55-131): every item row of Y is scored as
+ * (float) (sum over the query's users of SimpleVectorMath.dot(y_i, x_u) / n_users), bit-identical
+ * to the reference's arithmetic, and the best `how_many` come back ordered by value descending,
+ * equal values by ascending item (ByValueAscComparator reversed).  Filtered, like the reference:
+ * consider_known_items == 0 removes the intersection of the known items (the users' rows of R)
+ * of those users that have any (:396-425); `exclude` lists further items to skip (the tag IDs /
+ * IDRescorer.isFiltered of the caller; the callbacks themselves stay in the host language).
+ * out_items / out_values: how_many entries, *out_count of them valid.  1 <= how_many <= 256,
+ * 1 <= n_users <= 32.  ALS_E_NONFINITE: "Bad recommendation value" (RecommendIterator.java:99). */
+int als_recommend(als_handle *h, const int32_t *users, int32_t n_users, int32_t how_many,
+                  int32_t consider_known_items, const int32_t *exclude, int32_t n_exclude,
+                  int32_t *out_items, float *out_values, int32_t *out_count);
+/* One single-user query per entry of `users` (the loop of AllRecommendations.call,
+ * web-common/src/net/myrrix/web/AllRecommendations.java:77-117): four queries share each pass
+ * over Y.  out_items / out_values: [n_queries][how_many], out_counts: [n_queries]. */
+int als_recommend_batch(als_handle *h, const int32_t *users, int64_t n_queries, int32_t how_many,
+                        int32_t consider_known_items, int32_t *out_items, float *out_values,
+                        int32_t *out_counts);
+/* The same scoring for caller-supplied feature vectors (features: host, [n_vectors][features]):
+ * which = 1 scores the item rows (recommendToAnonymous, ServerRecommender.java:511-560, after the
+ * caller's fold-in), which = 0 the user rows. */
+int als_top_n(als_handle *h, int32_t which, const float *features, int32_t n_vectors,
+              const int32_t *exclude, int32_t n_exclude, int32_t how_many, int32_t *out_ids,
+              float *out_values, int32_t *out_count);
+
 /* ---- multi-GPU: one process per GPU, user/item ranges sharded over ranks ----- */
 /* Size in bytes of the opaque NCCL unique id, and creation of one (rank 0). */
 int als_comm_unique_id_size(void);

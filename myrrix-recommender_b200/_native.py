@@ -77,6 +77,11 @@ SYMBOLS = [
     ("als_get_interactions_by_column", C.c_int, [_H, _i64p, _i32p, _f32p]),
     ("als_get_interaction_rows", C.c_int, [_H, C.c_int32, C.c_int64, C.c_int64, _i64p, _i32p, _f32p,
                                            C.c_int64]),
+    ("als_recommend", C.c_int, [_H, _i32p, C.c_int32, C.c_int32, C.c_int32, _i32p, C.c_int32, _i32p, _f32p,
+                                _i32p]),
+    ("als_recommend_batch", C.c_int, [_H, _i32p, C.c_int64, C.c_int32, C.c_int32, _i32p, _f32p, _i32p]),
+    ("als_top_n", C.c_int, [_H, C.c_int32, _f32p, C.c_int32, _i32p, C.c_int32, C.c_int32, _i32p, _f32p,
+                            _i32p]),
     ("als_comm_unique_id_size", C.c_int, []),
     ("als_comm_get_unique_id", C.c_int, [C.c_void_p]),
     ("als_comm_init", C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),

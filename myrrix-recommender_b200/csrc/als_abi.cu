@@ -80,8 +80,11 @@ struct Csr {
   long long row_begin = 0;   // global index of local row 0
 };
 
+struct TopNState;  // topn_abi.cuh
+
 struct als_handle {
   als_config cfg;
+  TopNState* topn = nullptr;  // top-N scoring scratch, created on first use
   int k = 0, ks = 0;
   int kernel = ALS_KERNEL_SIMT;
   int device = 0;
@@ -194,6 +197,10 @@ void free_csr(als_handle* h, Csr* c) {
 }
 
 long long block_rows(long long n, int world) { return (n + world - 1) / world; }
+
+}  // namespace
+#include "topn_abi.cuh"
+namespace {
 
 void close_peers(als_handle* h) {
   for (int r = 0; r < 16; r++) {
@@ -980,6 +987,7 @@ int als_destroy(als_handle* h) {
     }
   }
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+  topn_free(h);
   free_csr(h, &h->by_user);
   free_csr(h, &h->by_item);
   cudaFree(h->X); cudaFree(h->Y); cudaFree(h->G); cudaFree(h->G_partial);

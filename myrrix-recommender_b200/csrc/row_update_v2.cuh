@@ -81,6 +81,13 @@ constexpr unsigned kFull = 0xffffffffu;
 #define ALS_V2_XSLOTS 0
 #endif
 
+// 1: hand-offs signalled by one elected lane per warp (after the warp's fences + __syncwarp) instead
+// of one mbarrier arrival per lane: 32x fewer SYNCS operations on `full`, `acc_empty`, `w_full`
+#ifndef ALS_V2_ARRIVE1
+#define ALS_V2_ARRIVE1 0
+#endif
+constexpr bool kArrive1 = ALS_V2_ARRIVE1 != 0;
+
 // 1: asynchronous gathers into the ring by a loader warp, in-place conversion; 0: register gathers (LDG)
 #ifndef ALS_V2_TMA
 #define ALS_V2_TMA 1
@@ -336,19 +343,19 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
 
   if (tid == 0) {
     for (int i = 0; i < kStages; i++) {
-      mbar_init(&full[i], 32);  // the 32 lanes of the producer warp that owns the stage
+      mbar_init(&full[i], kArrive1 ? 1 : 32);  // the producer warp that owns the stage (every lane, or one elected)
       mbar_init(&empty[i], 1);
       mbar_init(&raw_full[i], 32);  // copy-completion arrivals of the 32 lanes that gathered the stage
     }
     for (int i = 0; i < kAccSlots; i++) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], kArrive1 ? 4 : 128);
     }
     // W hand-off barriers are per SLOT (row u -> slot u % kWSlots): the drain sees every phase of
     // a slot's barriers in order, and phase n+1 of w_full cannot complete before the one waiter
     // of phase n (the Cholesky warp of row n * kWSlots + slot) has released the slot.
     for (int i = 0; i < kWSlots; i++) {
-      mbar_init(&w_full[i], 128);
+      mbar_init(&w_full[i], kArrive1 ? 4 : 128);
       mbar_init(&w_empty[i], 1);
     }
     // rhs hand-off barriers per rhs slot (row u -> slot u % kBSlots), same argument
@@ -522,7 +529,12 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
             bacc = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           fence_proxy_async_smem();
-          mbar_arrive(&full[slot]);
+          if (kArrive1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[slot]);
+          } else {
+            mbar_arrive(&full[slot]);
+          }
           f += P;
           slot += P;
           if (slot >= (uint32_t)kStages) { slot -= kStages; par ^= 1u; }
@@ -646,7 +658,12 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
           bacc = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         fence_proxy_async_smem();
-        mbar_arrive(&full[slot]);
+        if (kArrive1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[slot]);
+        } else {
+          mbar_arrive(&full[slot]);
+        }
         f += P;
         slot += P;
         if (slot >= (uint32_t)kStages) { slot -= kStages; par ^= 1u; }
@@ -785,9 +802,19 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
             }
           }
           tc_fence_before_sync();
-          mbar_arrive(&acc_empty[a]);  // accumulator may be overwritten by the next segment
+          if (kArrive1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+          } else {
+            mbar_arrive(&acc_empty[a]);  // accumulator may be overwritten by the next segment
+          }
         }
-        mbar_arrive(&w_full[ws]);  // 128 arrivals: the slot of this row is complete
+        if (kArrive1) {
+          __syncwarp();  // (orders every lane's slot stores before the elected lane's release)
+          if (lane == 0) mbar_arrive(&w_full[ws]);
+        } else {
+          mbar_arrive(&w_full[ws]);  // 128 arrivals: the slot of this row is complete
+        }
         useq++;
       }
     }

@@ -72,8 +72,22 @@ __device__ __forceinline__ void mbar_wait_id(uint64_t* bar, uint32_t parity, int
   }
 }
 #else
-__device__ __forceinline__ void mbar_wait_id(uint64_t* bar, uint32_t parity, int) {
-  mbar_wait(bar, parity);
+// Waits of the roles that run AHEAD of the pipeline (a full ring, no free accumulator / slot:
+// ids in ALS_BACKOFF_IDS) back off with an explicit sleep between polls: try_wait's own suspend
+// ends at every mbarrier event of the CTA (dozens of polls per wait), and those polls take issue
+// slots from the warps the waiter is waiting for.
+#ifndef ALS_BACKOFF_NS
+#define ALS_BACKOFF_NS 0
+#endif
+#ifndef ALS_BACKOFF_IDS
+#define ALS_BACKOFF_IDS ((1u << 0) | (1u << 1) | (1u << 2) | (1u << 4))  // b_empty, empty, acc_empty, w_empty
+#endif
+__device__ __forceinline__ void mbar_wait_id(uint64_t* bar, uint32_t parity, int id) {
+  if (ALS_BACKOFF_NS > 0 && ((ALS_BACKOFF_IDS >> id) & 1u)) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ALS_BACKOFF_NS);
+  } else {
+    mbar_wait(bar, parity);
+  }
 }
 #endif
 

@@ -253,6 +253,48 @@ class NativeALS:
                                       out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
 
+    # -- top-N scoring on the resident model (include/myrrix_als.h, csrc/topn.cuh) --------------
+    @staticmethod
+    def _i32(a):
+        a = np.ascontiguousarray(a, dtype=np.int32).reshape(-1)
+        return a, a.ctypes.data_as(C.POINTER(C.c_int32))
+
+    def recommend(self, users, how_many, consider_known_items=False, exclude=()):
+        """ServerRecommender.recommendToMany on dense indices: (items, values), best first."""
+        users, pu = self._i32(np.atleast_1d(users))
+        ex, pe = self._i32(exclude)
+        items = np.empty(how_many, dtype=np.int32)
+        values = np.empty(how_many, dtype=np.float32)
+        n = C.c_int32(0)
+        self.check(self.lib.als_recommend(self.h, pu, users.size, how_many, int(bool(consider_known_items)),
+                                          pe if ex.size else None, ex.size,
+                                          items.ctypes.data_as(C.POINTER(C.c_int32)), _fp(values), C.byref(n)))
+        return items[:n.value].copy(), values[:n.value].copy()
+
+    def recommend_batch(self, users, how_many, consider_known_items=False):
+        """One single-user query per entry (AllRecommendations): items [n][how_many] (-1 beyond
+        counts[n]), values, counts."""
+        users, pu = self._i32(users)
+        items = np.empty((users.size, how_many), dtype=np.int32)
+        values = np.empty((users.size, how_many), dtype=np.float32)
+        counts = np.empty(users.size, dtype=np.int32)
+        self.check(self.lib.als_recommend_batch(self.h, pu, users.size, how_many, int(bool(consider_known_items)),
+                                                items.ctypes.data_as(C.POINTER(C.c_int32)), _fp(values),
+                                                counts.ctypes.data_as(C.POINTER(C.c_int32))))
+        return items, values, counts
+
+    def top_n(self, which, features, how_many, exclude=()):
+        """Best rows of Y (which = 1 / "y") or X for the mean score of the given feature vectors."""
+        f = np.ascontiguousarray(features, dtype=np.float32).reshape(-1, self.features)
+        ex, pe = self._i32(exclude)
+        ids = np.empty(how_many, dtype=np.int32)
+        values = np.empty(how_many, dtype=np.float32)
+        n = C.c_int32(0)
+        self.check(self.lib.als_top_n(self.h, 0 if which in (0, "x", "X") else 1, _fp(f), f.shape[0],
+                                      pe if ex.size else None, ex.size, how_many,
+                                      ids.ctypes.data_as(C.POINTER(C.c_int32)), _fp(values), C.byref(n)))
+        return ids[:n.value].copy(), values[:n.value].copy()
+
     def gramian(self, which):
         out = np.zeros((self.features, self.features), dtype=np.float64)
         self.check(self.lib.als_gramian(self.h, 0 if which in (0, "x", "X") else 1,
