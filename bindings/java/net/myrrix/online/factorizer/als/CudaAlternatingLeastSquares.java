@@ -98,6 +98,9 @@ public final class CudaAlternatingLeastSquares implements MatrixFactorizer {
   private static native int nHalfY(long handle);
   private static native int nSync(long handle);
   private static native int nProbe(long handle, int[] users, int[] items, double[] out);
+  private static native int nCall(long handle, int[] testUsers, int[] testItems, int maxIterations,
+                                  double convergenceThreshold, boolean randomY, boolean xIsEmpty,
+                                  int[] iterationsRun, double[] lastConvergenceValue);
   private static native int nGetX(long handle, long outAddr);
   private static native int nGetY(long handle, long outAddr);
   private static native String nLastError(long handle);
@@ -205,6 +208,14 @@ public final class CudaAlternatingLeastSquares implements MatrixFactorizer {
       // RandomUtils.chooseAboutNFromStream over the key sets (ALS.java:206-214)
       int[] testUsers = sample(RbyRow.keySetIterator(), RbyRow.size(), userIndex, random);
       int[] testItems = sample(RbyColumn.keySetIterator(), RbyColumn.size(), itemIndex, random);
+      if (!Boolean.parseBoolean(System.getProperty("model.als.hostStopRule", "false"))) {
+        // the loop below, run by the library in one call with the statistic evaluated on the device
+        // (als_call); row-update errors (ALS_E_SINGULAR, ...) come back from it
+        check(h, nCall(h, testUsers, testItems, maxIterations, estimateErrorConvergenceThreshold, randomY, true,
+                       new int[1], new double[1]));
+        copyOut(h, userIDs, itemIDs, initialY);
+        return null;
+      }
       double[] estimates = new double[testUsers.length * testItems.length];  // X empty: zeros (:215-223)
       double[] fresh = new double[estimates.length];
       int iterationNumber = 0;

@@ -92,6 +92,24 @@ JNIEXPORT jint JNICALL CLS(nProbe)(JNIEnv *env, jclass c, jlong h, jintArray use
   return rc;
 }
 
+JNIEXPORT jint JNICALL CLS(nCall)(JNIEnv *env, jclass c, jlong h, jintArray users, jintArray items,
+                                  jint maxIterations, jdouble threshold, jboolean randomY, jboolean xIsEmpty,
+                                  jintArray iterationsRun, jdoubleArray lastValue) {
+  jint nu = (*env)->GetArrayLength(env, users), ni = (*env)->GetArrayLength(env, items);
+  jint *u = (*env)->GetIntArrayElements(env, users, NULL);
+  jint *i = (*env)->GetIntArrayElements(env, items, NULL);
+  int32_t it = 0;
+  double value = 0.0;
+  int rc = als_call(H(h), (const int32_t *)u, nu, (const int32_t *)i, ni, maxIterations, threshold,
+                    randomY ? 1 : 0, xIsEmpty ? 1 : 0, &it, &value);
+  (*env)->ReleaseIntArrayElements(env, users, u, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, items, i, JNI_ABORT);
+  jint jit = it;
+  (*env)->SetIntArrayRegion(env, iterationsRun, 0, 1, &jit);
+  (*env)->SetDoubleArrayRegion(env, lastValue, 0, 1, &value);
+  return rc;
+}
+
 JNIEXPORT jint JNICALL CLS(nGetX)(JNIEnv *env, jclass c, jlong h, jlong out) {
   return als_get_x(H(h), P(float, out));
 }

@@ -227,6 +227,19 @@ int als_get_interaction_rows(als_handle *h, int32_t by_column, int64_t first_row
                              int64_t *row_ptr_out, int32_t *idx_out, float *val_out,
                              int64_t capacity);
 
+/* AlternatingLeastSquares.call's iteration loop (AlternatingLeastSquares.java:206-257) in one
+ * call: X<-Y, Y<-X, then the convergence statistic -- the DoubleWeightedMean of |new - old| estimate
+ * weighted by max(0, new) over test_users x test_items (:232-240), evaluated on the device -- until
+ * the iteration limit (max_iterations > 0, :242-245), a non-finite statistic (:248-251) or
+ * statistic < convergence_threshold, except after iteration 1 of a build that started from a random
+ * Y (random_y != 0, :253-256).  The test IDs are the caller's choice (chooseAboutNFromStream walks
+ * the caller's maps, :206-213); x_is_empty != 0: first ever build, estimates start at 0 (:215-223).
+ * Outputs may be NULL.  Errors of a row update (ALS_E_SINGULAR, ...) come back from this call. */
+int als_call(als_handle *h, const int32_t *test_users, int32_t n_test_users,
+             const int32_t *test_items, int32_t n_test_items, int32_t max_iterations,
+             double convergence_threshold, int32_t random_y, int32_t x_is_empty,
+             int32_t *iterations_run, double *last_convergence_value);
+
 /* ---- top-N scoring on the resident model ------------------- */
 /* Replaces, for dense indices, ServerRecommender.recommend / recommendToMany
  * (online/src/net/myrrix/online/ServerRecommender.java:355-441) -> multithreadedTopN (:443-509)

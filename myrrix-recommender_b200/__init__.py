@@ -6,9 +6,10 @@ the host-side mirror of the reference interface
  online/src/net/myrrix/online/factorizer/als/AlternatingLeastSquares.java:66) that the
 parity tests and bench.py drive.  No CPU compute path exists here.
 """
-from . import _native, foldin, ingest, model_io
+from . import _native, foldin, ingest, initial_y, model_io, recommender
 from .factorizer import (AlternatingLeastSquares, MatrixFactorizer, NativeALS,
                          SingularMatrixSolverException, SolverException, properties)
 
 __all__ = ["AlternatingLeastSquares", "MatrixFactorizer", "NativeALS",
-           "SingularMatrixSolverException", "SolverException", "properties", "_native", "ingest", "foldin", "model_io"]
+           "SingularMatrixSolverException", "SolverException", "properties", "_native", "ingest", "foldin", "model_io",
+           "initial_y", "recommender"]

@@ -77,6 +77,8 @@ SYMBOLS = [
     ("als_get_interactions_by_column", C.c_int, [_H, _i64p, _i32p, _f32p]),
     ("als_get_interaction_rows", C.c_int, [_H, C.c_int32, C.c_int64, C.c_int64, _i64p, _i32p, _f32p,
                                            C.c_int64]),
+    ("als_call", C.c_int, [_H, _i32p, C.c_int32, _i32p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32,
+                           _i32p, _f64p]),
     ("als_recommend", C.c_int, [_H, _i32p, C.c_int32, C.c_int32, C.c_int32, _i32p, C.c_int32, _i32p, _f32p,
                                 _i32p]),
     ("als_recommend_batch", C.c_int, [_H, _i32p, C.c_int64, C.c_int32, C.c_int32, _i32p, _f32p, _i32p]),

@@ -78,7 +78,24 @@ def build_model_io(force=False):
     return MODEL_IO_LIB
 
 
+INIT_SRC = os.path.join(HERE, "csrc_host", "initial_y.cpp")
+INIT_LIB = os.path.join(HERE, "libmyrrix_init.so")
+
+
+def build_init(force=False):
+    """Host-only library (cold start: MersenneTwister stream, constructInitialY; include/myrrix_init.h).
+    -ffp-contract=off: the reference's float products are rounded before they are widened."""
+    hdr = os.path.join(os.path.dirname(HERE), "include", "myrrix_init.h")
+    if (not force and os.path.exists(INIT_LIB) and
+            all(os.path.getmtime(f) <= os.path.getmtime(INIT_LIB) for f in (INIT_SRC, hdr))):
+        return INIT_LIB
+    subprocess.check_call([CXX, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-o", INIT_LIB,
+                           INIT_SRC])
+    return INIT_LIB
+
+
 def build(force=False, verbose=False):
+    build_init(force)
     build_ingest(force)
     build_foldin(force)
     build_model_io(force)

@@ -1239,6 +1239,60 @@ int als_probe(als_handle* h, const int32_t* users, int32_t n_users, const int32_
   return ALS_OK;
 }
 
+// AlternatingLeastSquares.call's loop (ALS.java:206-257) with the stop rule on the device.
+int als_call(als_handle* h, const int32_t* test_users, int32_t n_test_users, const int32_t* test_items,
+             int32_t n_test_items, int32_t max_iterations, double convergence_threshold, int32_t random_y,
+             int32_t x_is_empty, int32_t* iterations_run, double* last_convergence_value) {
+  int rc = check_ready(h);
+  if (rc != ALS_OK) return rc;
+  if (n_test_users < 0 || n_test_items < 0 || (n_test_users > 0 && !test_users) || (n_test_items > 0 && !test_items))
+    return ALS_E_ARG;
+  if (!(convergence_threshold > 0.0 && convergence_threshold < 1.0))  // ALS.java:140
+    return fail(h, ALS_E_ARG, "convergence threshold must be in (0,1)");
+  const long long n = (long long)n_test_users * n_test_items;
+  if (n > 1000000) return fail(h, ALS_E_ARG, "too many convergence test pairs");
+  if (max_iterations <= 0 && n == 0) return fail(h, ALS_E_ARG, "no iteration limit and nothing to test convergence on");
+  if (iterations_run) *iterations_run = 0;
+  if (last_convergence_value) *last_convergence_value = NAN;
+  CU(h, cudaSetDevice(h->device));
+  double* d_est = nullptr;   // estimates[][] (:215), then the statistic
+  double* fresh = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  if (!fresh) return ALS_E_OOM;
+  if (cudaMalloc(&d_est, sizeof(double) * (size_t)(n + 2)) != cudaSuccess) { free(fresh); cudaGetLastError(); return fail(h, ALS_E_OOM, "stop-rule scratch"); }
+  auto done = [&](int code) { cudaFree(d_est); free(fresh); return code; };
+  cudaMemsetAsync(d_est, 0, sizeof(double) * (size_t)(n + 2), h->stream);
+  if (n > 0 && !x_is_empty) {
+    // estimates of the model as it stands (:216-222); als_probe leaves them in d_probe_out
+    if ((rc = als_probe(h, test_users, n_test_users, test_items, n_test_items, fresh)) != ALS_OK) return done(rc);
+    cudaMemcpyAsync(d_est, h->d_probe_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream);
+  }
+  int it = 0;
+  double value = NAN;
+  while (true) {
+    if ((rc = als_half_x(h)) != ALS_OK) return done(rc);   // :230
+    if ((rc = als_half_y(h)) != ALS_OK) return done(rc);   // :231
+    double stat[2] = {NAN, 0.0};
+    if (n > 0) {
+      if ((rc = als_probe(h, test_users, n_test_users, test_items, n_test_items, fresh)) != ALS_OK) return done(rc);
+      stop_rule_kernel<<<1, 32, 0, h->stream>>>(h->d_probe_out, d_est, (int)n, d_est + n);
+      h->launches += 1;
+      if (cudaMemcpyAsync(stat, d_est + n, sizeof(stat), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+          cudaStreamSynchronize(h->stream) != cudaSuccess)
+        return done(fail(h, ALS_E_CUDA, "stop rule: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    // a failed row (singular / non-finite) must surface now, not after more iterations
+    if ((rc = als_sync(h)) != ALS_OK) return done(rc);
+    it++;
+    value = stat[0];
+    if (iterations_run) *iterations_run = it;
+    if (last_convergence_value) *last_convergence_value = value;
+    if (max_iterations > 0 && it >= max_iterations) break;              // :242-245
+    if (!isfinite(value)) break;                                        // :248-251
+    if (!(random_y && it == 1) && value < convergence_threshold) break; // :253-256
+  }
+  return done(ALS_OK);
+}
+
 int als_gramian(als_handle* h, int32_t which, double* out) {
   int rc = check_ready(h);
   if (rc != ALS_OK) return rc;

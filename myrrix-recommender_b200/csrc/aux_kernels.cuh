@@ -73,6 +73,34 @@ __global__ void probe_kernel(const float* __restrict__ X, const float* __restric
   out[t] = dot;
 }
 
+// The stop rule's statistic (AlternatingLeastSquares.java:232-240) over the probe's fresh
+// estimates, on the device: DoubleWeightedMean.increment (common/.../stats/DoubleWeightedMean.java
+// :73-81) is an order-dependent fp64 recurrence, so ONE thread walks the (user, item) pairs in the
+// reference's order (at most ~1e4 pairs: about 0.2 ms per iteration).  estimates[] <- the new values.
+// out[0] = mean (getResult()), out[1] = total weight.
+__global__ void stop_rule_kernel(const double* __restrict__ fresh, double* __restrict__ estimates, int n,
+                                 double* __restrict__ out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double total_weight = 0.0, mean = 0.0;
+  for (int t = 0; t < n; t++) {
+    const double nv = fresh[t], ov = estimates[t];
+    estimates[t] = nv;
+    const double datum = fabs(nv - ov);       // FastMath.abs(newValue - oldValue)
+    const double weight = fmax(0.0, nv);      // FastMath.max(0.0, newValue): NaN stays NaN like Java's max
+    const double weight_j = (nv != nv) ? nv : weight;
+    const double old_total = total_weight;
+    total_weight = __dadd_rn(total_weight, weight_j);
+    if (old_total <= 0.0) {
+      mean = datum;
+    } else {
+      mean = __dadd_rn(__ddiv_rn(__dmul_rn(mean, old_total), total_weight),
+                       __ddiv_rn(__dmul_rn(datum, weight_j), total_weight));
+    }
+  }
+  out[0] = mean;
+  out[1] = total_weight;
+}
+
 // out[i][0..k) = F[rows[i]][0..k): selected factor rows, unpadded (als_get_rows)
 __global__ void gather_rows_kernel(const float* __restrict__ F, int ks, int k, const int* __restrict__ rows,
                                    int n, float* __restrict__ out) {

@@ -16,6 +16,7 @@ import math
 import numpy as np
 
 from . import _native as N
+from . import initial_y
 
 # JVM system properties the reference reads on this path, same names.
 properties = {}
@@ -244,6 +245,17 @@ class NativeALS:
     def sync(self):
         self.check(self.lib.als_sync(self.h))
 
+    def call(self, test_users, test_items, max_iterations, convergence_threshold, random_y, x_is_empty=True):
+        """The iteration loop of AlternatingLeastSquares.call with the stop rule on the device
+        (als_call): (iterations run, last convergence value)."""
+        tu, pu = self._i32(test_users)
+        ti, pi = self._i32(test_items)
+        n_it, val = C.c_int32(0), C.c_double(float("nan"))
+        self.check(self.lib.als_call(self.h, pu, tu.size, pi, ti.size, int(max_iterations),
+                                     float(convergence_threshold), int(bool(random_y)), int(bool(x_is_empty)),
+                                     C.byref(n_it), C.byref(val)))
+        return n_it.value, val.value
+
     def probe(self, users, items):
         users = np.ascontiguousarray(users, dtype=np.int32)
         items = np.ascontiguousarray(items, dtype=np.int32)
@@ -400,7 +412,7 @@ class AlternatingLeastSquares(MatrixFactorizer):
         self.previousY = None
         self.device = device
         self.kernel = kernel
-        self.random = random if random is not None else np.random.default_rng(1234567890)
+        self.random = random if random is not None else initial_y.RandomManager.getRandom()
         self.iterationsRun = 0
         self.lastConvergenceValue = float("nan")
 
@@ -417,66 +429,37 @@ class AlternatingLeastSquares(MatrixFactorizer):
         self.previousY = previousY
 
     # -- constructInitialY, ALS.java:264-335 ---------------------------------
-    def _random_unit_vector(self):
-        # RandomUtils.doRandomUnitVector (common/.../random/RandomUtils.java:88-100)
-        d = self.random.standard_normal(self.features)
-        v = d.astype(np.float32)
-        v /= np.float32(math.sqrt(float(np.dot(d, d))))
-        return v
-
-    def _random_unit_vector_far_from(self, far_from):
-        # RandomUtils.randomUnitVectorFarFrom (RandomUtils.java:110-140); the RNG stream is
-        # numpy's, not MersenneTwister's, so cold starts are statistically -- not bitwise --
-        # the reference's.
-        size = len(far_from)
-        num_samples = min(100, size)
-        while True:
-            v = self._random_unit_vector()
-            smallest = float("inf")
-            for s in range(num_samples):
-                other = far_from[s if size == num_samples else int(self.random.integers(size))]
-                dist2 = 2.0 - 2.0 * float(np.dot(v.astype(np.float64), other.astype(np.float64)))
-                if math.isfinite(dist2) and dist2 < smallest:
-                    smallest = dist2
-            if math.isfinite(smallest) and not (self.features == 1 and smallest == 0.0):
-                if self.random.random() < smallest / 4.0:
-                    return v
-            else:
-                return v
-
     def _construct_initial_y(self, previousY):
+        """Dense rows for every key of previousY and of RbyColumn, in their maps' iteration order,
+        then libmyrrix_init.so (include/myrrix_init.h) draws from the MersenneTwister stream exactly
+        like constructInitialY / randomUnitVectorFarFrom; the dict comes back keyed like the maps."""
         k = self.features
         if not previousY:
-            randomY = {}
-        else:
-            old = len(next(iter(previousY.values())))
-            if old > k:  # ALS.java:277-287
-                randomY = {}
-                for key, vec in previousY.items():
-                    v = np.array(vec[:k], dtype=np.float32)
-                    v /= np.float32(math.sqrt(float(np.sum(v.astype(np.float64) ** 2))))
-                    randomY[key] = v
-            elif old < k:  # ALS.java:289-302
-                randomY = {}
-                for key, vec in previousY.items():
-                    v = np.zeros(k, dtype=np.float32)
-                    v[:old] = vec
-                    v[old:] = self.random.standard_normal(k - old).astype(np.float32)
-                    v /= np.float32(math.sqrt(float(np.sum(v.astype(np.float64) ** 2))))
-                    randomY[key] = v
-            else:  # adopt in place, ALS.java:304-308
-                randomY = previousY
-        recent = []
-        for vec in randomY.values():
-            if len(recent) >= 100000:
-                break
-            recent.append(np.asarray(vec, dtype=np.float32))
+            previousY = {}
+        keys = list(previousY.keys())
+        index = {key: i for i, key in enumerate(keys)}
         for item_id in self.RbyColumn.keys():
-            if item_id not in randomY:
-                v = self._random_unit_vector_far_from(recent)
-                randomY[item_id] = v
-                if len(recent) < 100000:
-                    recent.append(v)
+            if item_id not in index:
+                index[item_id] = len(keys)
+                keys.append(item_id)
+        prev = None
+        if previousY:
+            old = len(next(iter(previousY.values())))
+            prev = np.zeros((len(keys), old), dtype=np.float32)
+            for key, vec in previousY.items():
+                prev[index[key]] = vec
+            if old == k:
+                randomY = previousY  # adopted in place (ALS.java:304-308): only new keys are added
+            else:
+                randomY = {}
+        else:
+            randomY = {}
+        y, has = initial_y.construct_initial_y(
+            self.random, k, len(keys), [index[i] for i in self.RbyColumn.keys()], prev,
+            [index[key] for key in previousY.keys()])
+        for key in keys:
+            if key not in randomY and has[index[key]]:
+                randomY[key] = y[index[key]].copy()
         return randomY
 
     # -- flattening: long IDs -> dense indices, maps -> CSR --------------------
@@ -501,7 +484,7 @@ class AlternatingLeastSquares(MatrixFactorizer):
         keys = list(keys)
         if n < len(keys):
             rate = float(n) / len(keys)
-            keys = [key for key in keys if self.random.random() < rate]
+            keys = [key for key in keys if self.random.nextDouble() < rate]
         return keys
 
     def call(self):
@@ -570,6 +553,15 @@ class AlternatingLeastSquares(MatrixFactorizer):
             tu = np.array([uindex[u] for u in test_users], dtype=np.int32)
             ti = np.array([iindex[it] for it in test_items], dtype=np.int32)
             estimates = np.zeros((tu.size, ti.size), dtype=np.float64)  # X empty: stay 0 (:215-223)
+
+            if not _prop_bool("model.als.hostStopRule"):
+                # the loop below, run by the library with the statistic computed on the device
+                self.iterationsRun, conv = als.call(tu, ti, self.maxIterations,
+                                                    self.estimateErrorConvergenceThreshold, randomY)
+                if not (self.maxIterations > 0 and self.iterationsRun >= self.maxIterations):
+                    self.lastConvergenceValue = conv
+                publish()
+                return None
 
             iterationNumber = 0
             while True:

@@ -588,3 +588,32 @@ def test_headline_cutdown_full_parity_five_iterations(M, O):
     for name, a, b in (("X", X, Xo), ("Y", Y, Yo)):
         fro, mx = rel_err(a, b)
         assert fro <= TOL and mx <= TOL, (name, fro, mx)
+
+
+@pytest.mark.gpu
+def test_device_stop_rule_equals_host_stop_rule(M, goldens):
+    """als_call (stop rule evaluated on the device, ALS.java:230-257) stops after the same
+    iteration with the same DoubleWeightedMean as the host loop over als_probe."""
+    for name, recon in (("als", False), ("als", True), ("negative_input", False)):
+        g = goldens[name]
+        runs = []
+        for host_rule in (False, True):
+            by_row, by_col = dense_to_maps(g["R"])
+            prevY = {i: np.array(v, np.float32) for i, v in enumerate(g["Y0"])}
+            M.properties.clear()
+            if recon:
+                M.properties["model.reconstructRMatrix"] = "true"
+            if host_rule:
+                M.properties["model.als.hostStopRule"] = "true"
+            try:
+                als = M.AlternatingLeastSquares(by_row, by_col, g["features"], g["threshold"],
+                                                g["max_iterations"])
+                als.setPreviousY(prevY)
+                als.call()
+            finally:
+                M.properties.clear()
+            runs.append((als.iterationsRun, als.lastConvergenceValue,
+                         np.stack([als.getX()[u] for u in sorted(als.getX())])))
+        assert runs[0][0] == runs[1][0]
+        assert runs[0][1] == runs[1][1]  # bit-identical statistic
+        assert np.array_equal(runs[0][2], runs[1][2])
