@@ -453,8 +453,8 @@ int configure_kernels(als_handle* h) {
   if (h->ks == 32) {
     if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<32, 4>, umma::Smem<32, 4>::kTotal)) != ALS_OK) return rc;
     if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<32, 8>, umma::Smem<32, 8>::kTotal)) != ALS_OK) return rc;
-    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<32, v2::MixLong>, v2::Smem<32, v2::MixLong>::kTotal)) != ALS_OK) return rc;
-    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<32, v2::MixShort>, v2::Smem<32, v2::MixShort>::kTotal)) != ALS_OK) return rc;
+    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<32, v2::Mixes<32>::Long>, v2::Smem<32, v2::Mixes<32>::Long>::kTotal)) != ALS_OK) return rc;
+    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<32, v2::Mixes<32>::Short>, v2::Smem<32, v2::Mixes<32>::Short>::kTotal)) != ALS_OK) return rc;
   } else if (h->ks == 64) {
     if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<64, 4>, umma::Smem<64, 4>::kTotal)) != ALS_OK) return rc;
     if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<64, 8>, umma::Smem<64, 8>::kTotal)) != ALS_OK) return rc;
@@ -517,8 +517,8 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
       rc = long_rows ? launch_row_update_v2_t<64, v2::MixLong>(p, h->sm_count, h->stream, h->err, sizeof(h->err))
                      : launch_row_update_v2_t<64, v2::MixShort>(p, h->sm_count, h->stream, h->err, sizeof(h->err));
     } else if (h->ks == 32 && !h->legacy_umma) {
-      rc = long_rows ? launch_row_update_v2_t<32, v2::MixLong>(p, h->sm_count, h->stream, h->err, sizeof(h->err))
-                     : launch_row_update_v2_t<32, v2::MixShort>(p, h->sm_count, h->stream, h->err, sizeof(h->err));
+      rc = long_rows ? launch_row_update_v2_t<32, v2::Mixes<32>::Long>(p, h->sm_count, h->stream, h->err, sizeof(h->err))
+                     : launch_row_update_v2_t<32, v2::Mixes<32>::Short>(p, h->sm_count, h->stream, h->err, sizeof(h->err));
     } else {
       rc = launch_row_update_umma(h->ks, p, long_rows, h->sm_count, h->stream, h->err, sizeof(h->err));
     }

@@ -81,6 +81,12 @@ constexpr unsigned kFull = 0xffffffffu;
 #define ALS_V2_XSLOTS 0
 #endif
 
+// extra own-stages of look-ahead for a producer's index / value loads (see the producer loop)
+#ifndef ALS_V2_FETCH_EXTRA
+#define ALS_V2_FETCH_EXTRA 0
+#endif
+constexpr int kFetchExtra = ALS_V2_FETCH_EXTRA;
+
 // 1: hand-offs signalled by one elected lane per warp (after the warp's fences + __syncwarp) instead
 // of one mbarrier arrival per lane: 32x fewer SYNCS operations on `full`, `acc_empty`, `w_full`
 #ifndef ALS_V2_ARRIVE1
@@ -157,6 +163,34 @@ struct Mix {
 #endif
 using MixShort = Mix<ALS_V2_S_NCHOL, ALS_V2_S_NPROD, ALS_V2_S_STAGES, ALS_V2_S_AHEAD, ALS_V2_S_SETREG != 0, ALS_V2_S_ASYNC != 0>;
 using MixLong = Mix<ALS_V2_L_NCHOL, ALS_V2_L_NPROD, ALS_V2_L_STAGES, ALS_V2_L_AHEAD, ALS_V2_L_SETREG != 0, ALS_V2_L_ASYNC != 0>;
+// k = 32: a solve is 4x cheaper and its slot 3 KB instead of 10 KB; the mixes are tuned separately
+// (ALS_V2_S32_* / ALS_V2_L32_*)
+// (short rows, measured on config 2, X-half: 8 + 7 warps with setmaxnreg 5.3 ms; 12 + 7 warps at the
+// launch register count 4.9 ms; 16 + 7: 4.9 ms; 8 + 11 or 12 + 11: 5.1-5.3 ms)
+#ifndef ALS_V2_S32_NCHOL
+#define ALS_V2_S32_NCHOL 12
+#define ALS_V2_S32_NPROD 7
+#define ALS_V2_S32_STAGES 24
+#define ALS_V2_S32_AHEAD 2
+#define ALS_V2_S32_SETREG 0
+#endif
+#ifndef ALS_V2_L32_NCHOL
+#define ALS_V2_L32_NCHOL ALS_V2_L_NCHOL
+#define ALS_V2_L32_NPROD ALS_V2_L_NPROD
+#define ALS_V2_L32_STAGES ALS_V2_L_STAGES
+#define ALS_V2_L32_AHEAD ALS_V2_L_AHEAD
+#define ALS_V2_L32_SETREG ALS_V2_L_SETREG
+#endif
+template <int KS>
+struct Mixes {
+  using Short = MixShort;
+  using Long = MixLong;
+};
+template <>
+struct Mixes<32> {
+  using Short = Mix<ALS_V2_S32_NCHOL, ALS_V2_S32_NPROD, ALS_V2_S32_STAGES, ALS_V2_S32_AHEAD, ALS_V2_S32_SETREG != 0, true>;
+  using Long = Mix<ALS_V2_L32_NCHOL, ALS_V2_L32_NPROD, ALS_V2_L32_STAGES, ALS_V2_L32_AHEAD, ALS_V2_L32_SETREG != 0, true>;
+};
 
 template <int KS, class MX>
 struct Smem {
@@ -398,6 +432,9 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
     const int sub = lane / CPR;  // which of the RPP entries of a pass
     const int el0 = lane % E;    // entry whose index / value / scalars this lane holds
     constexpr int D = MX::kAhead;
+    // index / value queue depth: the entries of a stage are fetched (HBM latency: ~1.5k cycles)
+    // kFetchExtra + 1 own-stages before its gather is issued
+    constexpr int QD = D + 1 + kFetchExtra;
     uint32_t oh0, ol0;
     G::slots(sub, q, oh0, ol0);  // pass 0; lo = hi ^ 32
     const uint32_t ring_a = smem_u32(ring);
@@ -442,10 +479,10 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
       };
       // queue of my next D + 1 stages' (index, value): position d <-> stage f + d * P; shifted
       // down by one every step (a few register moves instead of D + 1 unrolled loop bodies)
-      int q_idx[D + 1];
-      float q_val[D + 1];
+      int q_idx[QD];
+      float q_val[QD];
 #pragma unroll
-      for (int d = 0; d <= D; d++) fetch(f + (uint32_t)(d * P), q_idx[d], q_val[d]);
+      for (int d = 0; d < QD; d++) fetch(f + (uint32_t)(d * P), q_idx[d], q_val[d]);
       uint32_t gslot = slot, gpar = par;  // ring position of the next stage to gather
 #pragma unroll
       for (int d = 0; d < D; d++) {
@@ -463,8 +500,8 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
           if (gslot >= (uint32_t)kStages) { gslot -= kStages; gpar ^= 1u; }
           // (2) shift the queue; indices / values of the stage after that into its last position
 #pragma unroll
-          for (int d = 0; d < D; d++) { q_idx[d] = q_idx[d + 1]; q_val[d] = q_val[d + 1]; }
-          fetch(f + (uint32_t)((D + 1) * P), q_idx[D], q_val[D]);
+          for (int d = 0; d < QD - 1; d++) { q_idx[d] = q_idx[d + 1]; q_val[d] = q_val[d + 1]; }
+          fetch(f + (uint32_t)(QD * P), q_idx[QD - 1], q_val[QD - 1]);
           // (3) my current stage
           const int i = __ffs(__ballot_sync(kFull, B.end > f)) - 1;
           const int cnt = __shfl_sync(kFull, B.cnt, i);

@@ -24,6 +24,8 @@ names = ["prod:b_empty", "prod:empty", "mma:acc_empty", "mma:full", "drain:w_emp
          "chol:w_full", "chol:b_full", "kernel total (per CTA sum)", "chol:lockstep", "chol:factor_solve",
          "prod:raw_full"]
 warps = [7, 7, 1, 1, 4, 4, 8, 8, 1, 8, 8, 7]
+if name == "c2":
+    warps = [7, 7, 1, 1, 4, 4, 12, 12, 1, 12, 12, 7]
 with M.NativeALS(k) as als:
     als.synth_interactions(U, I, nnz, seed=1234567890)
     als.synth_y0(seed=1234567890)
