@@ -240,6 +240,22 @@ int als_call(als_handle *h, const int32_t *test_users, int32_t n_test_users,
              double convergence_threshold, int32_t random_y, int32_t x_is_empty,
              int32_t *iterations_run, double *last_convergence_value);
 
+/* ---- the live model between builds ------------------------- */
+/* Generation.recomputeState (online/src/net/myrrix/online/generation/Generation.java:132-158) for a
+ * model that stays in HBM: als_gramian gives X'X / Y'Y from the resident factors, libmyrrix_foldin.so
+ * (myrrix_foldin.h) applies the infNorm guard and factorises them once per generation, and this call
+ * keeps a copy of the factors (foldin_export_solver) on the device.  which: 0 = X'X solver,
+ * 1 = Y'Y solver; qrt == NULL: no solver for that side (model.solver.xtx.compute=false).
+ * learn_rate: model.foldin.learningRate. */
+int als_set_fold_in_state(als_handle *h, int32_t which, const double *qrt, const double *rdiag,
+                          const int32_t *perm, double learn_rate);
+/* ServerRecommender.updateFeatures (online/.../ServerRecommender.java:865-907) for n writes
+ * (user, item, value; values == NULL: all 1.0), applied in order to the resident rows of X and Y:
+ * each write sees what the previous ones left, like the reference's one-call-at-a-time stream.
+ * als_recommend and als_get_rows see the updated rows at once. */
+int als_fold_in(als_handle *h, const int32_t *users, const int32_t *items, const float *values,
+                int64_t n);
+
 /* ---- top-N scoring on the resident model ------------------- */
 /* Replaces, for dense indices, ServerRecommender.recommend / recommendToMany
  * (online/src/net/myrrix/online/ServerRecommender.java:355-441) -> multithreadedTopN (:443-509)

@@ -56,6 +56,10 @@ int foldin_update_features(const foldin_handle* h, float* user_features, float* 
  * does this one setPreference call at a time (ServerRecommender.java:735-760, bulk ingest). */
 int foldin_update_many(const foldin_handle* h, float* X, float* Y, const int32_t* users,
                        const int32_t* items, const float* values, int64_t n);
+/* The factors of one solver, for a device-side copy (als_set_fold_in_state in myrrix_als.h):
+ * qrt [k][k] (row `minor` = Householder vector / R column of step `minor`), rdiag [k] (R's
+ * diagonal), perm [k] (perm[j] = original column now at position j). */
+int foldin_export_solver(const foldin_handle* h, int32_t which, double* qrt, double* rdiag, int32_t* perm);
 /* buildAnonymousUserFeatures over the n item rows that were found (row-major n x k); values may
  * be NULL (all 1.0). out: k floats. */
 int foldin_anonymous_user(const foldin_handle* h, const float* item_rows, const float* values, int32_t n,

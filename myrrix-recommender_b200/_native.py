@@ -79,6 +79,8 @@ SYMBOLS = [
                                            C.c_int64]),
     ("als_call", C.c_int, [_H, _i32p, C.c_int32, _i32p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32,
                            _i32p, _f64p]),
+    ("als_set_fold_in_state", C.c_int, [_H, C.c_int32, _f64p, _f64p, _i32p, C.c_double]),
+    ("als_fold_in", C.c_int, [_H, _i32p, _i32p, _f32p, C.c_int64]),
     ("als_recommend", C.c_int, [_H, _i32p, C.c_int32, C.c_int32, C.c_int32, _i32p, C.c_int32, _i32p, _f32p,
                                 _i32p]),
     ("als_recommend_batch", C.c_int, [_H, _i32p, C.c_int64, C.c_int32, C.c_int32, _i32p, _f32p, _i32p]),

@@ -14,6 +14,7 @@
 #include <new>
 
 #include "aux_kernels.cuh"
+#include "foldin_dev.cuh"
 #include "common.cuh"
 #include "gramian.cuh"
 #include "row_update_simt.cuh"
@@ -85,6 +86,11 @@ struct TopNState;  // topn_abi.cuh
 struct als_handle {
   als_config cfg;
   TopNState* topn = nullptr;  // top-N scoring scratch, created on first use
+  // fold-in solver state of the generation (als_set_fold_in_state): [0] X'X, [1] Y'Y
+  double* fi_qrt[2] = {nullptr, nullptr};
+  double* fi_rdiag[2] = {nullptr, nullptr};
+  int* fi_perm[2] = {nullptr, nullptr};
+  double fi_learn_rate = 1.0;
   int k = 0, ks = 0;
   int kernel = ALS_KERNEL_SIMT;
   int device = 0;
@@ -988,6 +994,7 @@ int als_destroy(als_handle* h) {
   }
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   topn_free(h);
+  for (int w = 0; w < 2; w++) { cudaFree(h->fi_qrt[w]); cudaFree(h->fi_rdiag[w]); cudaFree(h->fi_perm[w]); }
   free_csr(h, &h->by_user);
   free_csr(h, &h->by_item);
   cudaFree(h->X); cudaFree(h->Y); cudaFree(h->G); cudaFree(h->G_partial);
@@ -1291,6 +1298,72 @@ int als_call(als_handle* h, const int32_t* test_users, int32_t n_test_users, con
     if (!(random_y && it == 1) && value < convergence_threshold) break; // :253-256
   }
   return done(ALS_OK);
+}
+
+// ---- fold-in on the resident rows (foldin_dev.cuh) ---------------------------------------------
+int als_set_fold_in_state(als_handle* h, int32_t which, const double* qrt, const double* rdiag,
+                          const int32_t* perm, double learn_rate) {
+  if (!h || (which != 0 && which != 1)) return ALS_E_ARG;
+  if (qrt && (!rdiag || !perm)) return ALS_E_ARG;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  cudaFree(h->fi_qrt[which]); cudaFree(h->fi_rdiag[which]); cudaFree(h->fi_perm[which]);
+  h->fi_qrt[which] = nullptr; h->fi_rdiag[which] = nullptr; h->fi_perm[which] = nullptr;
+  h->fi_learn_rate = learn_rate;
+  if (!qrt) return ALS_OK;  // "model.solver.xtx.compute=false": no solver for this side
+  const int k = h->k;
+  for (int i = 0; i < k; i++) {
+    if (perm[i] < 0 || perm[i] >= k) return fail(h, ALS_E_ARG, "fold-in state: bad permutation");
+    if (!(rdiag[i] == rdiag[i]) || rdiag[i] == 0.0) return fail(h, ALS_E_ARG, "fold-in state: singular R");
+  }
+  CU(h, cudaMalloc(&h->fi_qrt[which], sizeof(double) * (size_t)k * k));
+  CU(h, cudaMalloc(&h->fi_rdiag[which], sizeof(double) * (size_t)k));
+  CU(h, cudaMalloc(&h->fi_perm[which], sizeof(int) * (size_t)k));
+  CU(h, cudaMemcpyAsync(h->fi_qrt[which], qrt, sizeof(double) * (size_t)k * k, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->fi_rdiag[which], rdiag, sizeof(double) * (size_t)k, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->fi_perm[which], perm, sizeof(int) * (size_t)k, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return ALS_OK;
+}
+
+int als_fold_in(als_handle* h, const int32_t* users, const int32_t* items, const float* values, int64_t n) {
+  int rc = check_ready(h);
+  if (rc != ALS_OK) return rc;
+  if (n < 0 || (n > 0 && (!users || !items))) return ALS_E_ARG;
+  if (n == 0) return ALS_OK;
+  if (h->world > 1) return fail(h, ALS_E_UNSUPPORTED, "fold-in runs on a single-GPU handle (the serving replica)");
+  if (!h->fi_qrt[0] && !h->fi_qrt[1]) return fail(h, ALS_E_STATE, "no fold-in solver state (als_set_fold_in_state)");
+  for (int64_t e = 0; e < n; e++) {
+    if (users[e] < 0 || users[e] >= h->n_users) return fail(h, ALS_E_ARG, "fold-in user %d out of range", users[e]);
+    if (items[e] < 0 || items[e] >= h->n_items) return fail(h, ALS_E_ARG, "fold-in item %d out of range", items[e]);
+  }
+  CU(h, cudaSetDevice(h->device));
+  int* d_ui = nullptr;
+  float* d_v = nullptr;
+  CU(h, cudaMalloc(&d_ui, sizeof(int) * (size_t)(2 * n + 1)));
+  if (values && cudaMalloc(&d_v, sizeof(float) * (size_t)n) != cudaSuccess) { cudaFree(d_ui); cudaGetLastError(); return fail(h, ALS_E_OOM, "fold-in scratch"); }
+  cudaMemcpyAsync(d_ui, users, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(d_ui + n, items, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+  if (values) cudaMemcpyAsync(d_v, values, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+  int* d_st = d_ui + 2 * n;
+  cudaMemsetAsync(d_st, 0, sizeof(int), h->stream);
+  FoldInSolver sx{h->fi_qrt[0], h->fi_rdiag[0], h->fi_perm[0]}, sy{h->fi_qrt[1], h->fi_rdiag[1], h->fi_perm[1]};
+  nvtxRangePushA("als:fold_in");
+  switch ((h->k + 31) / 32) {
+    case 1: fold_in_kernel<1><<<1, 64, 0, h->stream>>>(h->X, h->Y, h->ks, h->k, d_ui, d_ui + n, d_v, n, sx, sy, h->fi_learn_rate, d_st); break;
+    case 2: fold_in_kernel<2><<<1, 64, 0, h->stream>>>(h->X, h->Y, h->ks, h->k, d_ui, d_ui + n, d_v, n, sx, sy, h->fi_learn_rate, d_st); break;
+    case 3: fold_in_kernel<3><<<1, 64, 0, h->stream>>>(h->X, h->Y, h->ks, h->k, d_ui, d_ui + n, d_v, n, sx, sy, h->fi_learn_rate, d_st); break;
+    default: fold_in_kernel<4><<<1, 64, 0, h->stream>>>(h->X, h->Y, h->ks, h->k, d_ui, d_ui + n, d_v, n, sx, sy, h->fi_learn_rate, d_st); break;
+  }
+  nvtxRangePop();
+  h->launches += 1;
+  int st = 0;
+  cudaMemcpyAsync(&st, d_st, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_ui); cudaFree(d_v);
+  if (e != cudaSuccess) return fail(h, ALS_E_CUDA, "als_fold_in: %s", cudaGetErrorString(e));
+  if (st == ALS_E_NONFINITE) return fail(h, ALS_E_NONFINITE, "non-finite fold-in (ServerRecommender.java:872, :889)");
+  return ALS_OK;
 }
 
 int als_gramian(als_handle* h, int32_t which, double* out) {

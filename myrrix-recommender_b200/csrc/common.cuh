@@ -74,6 +74,21 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return d;
 }
 
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+  float2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+
 __host__ __device__ constexpr int round_up_int(int a, int b) { return (a + b - 1) / b * b; }
 
 // Padded feature count (row stride of the device factor matrices).

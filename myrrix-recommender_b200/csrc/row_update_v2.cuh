@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
     uint32_t slot = (uint32_t)pw, par = 0;  // its ring slot and phase parity
     uint32_t base = 0;
     int useq_base = 0;
-    float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 bacc01 = make_float2(0.f, 0.f), bacc23 = make_float2(0.f, 0.f);
     const float alpha = p.alpha;
     const bool recon = p.reconstruct_r != 0;
     for (long long rb = blockIdx.x; rb < p.n_rows; rb += 32 * row_step) {
@@ -526,16 +526,19 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
           for (int ps = 0; ps < 8; ps++) {
             const float sc = __shfl_sync(kFull, my_s, sub + RPP * ps);
             const float cb = __shfl_sync(kFull, my_cb, sub + RPP * ps);
-            const float4 v = make_float4(y[ps].x * sc, y[ps].y * sc, y[ps].z * sc, y[ps].w * sc);
+            // packed fp32x2 arithmetic: scale, split, rhs (half the issue slots of the scalar form)
+            const float2 y01 = make_float2(y[ps].x, y[ps].y), y23 = make_float2(y[ps].z, y[ps].w);
+            const float2 sc2 = make_float2(sc, sc), cb2 = make_float2(cb, cb);
+            const float2 v01 = fmul2(y01, sc2), v23 = fmul2(y23, sc2);
             // bf16 hi + bf16 lo, round-to-nearest both times
-            const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y);
-            const __nv_bfloat162 h23 = __floats2bfloat162_rn(v.z, v.w);
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(v01.x, v01.y);
+            const __nv_bfloat162 h23 = __floats2bfloat162_rn(v23.x, v23.y);
             const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01);
             const uint32_t u23 = *reinterpret_cast<const uint32_t*>(&h23);
-            const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __uint_as_float(u01 << 16),
-                                                             v.y - __uint_as_float(u01 & 0xffff0000u));
-            const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __uint_as_float(u23 << 16),
-                                                             v.w - __uint_as_float(u23 & 0xffff0000u));
+            const float2 r01 = fsub2(v01, make_float2(__uint_as_float(u01 << 16), __uint_as_float(u01 & 0xffff0000u)));
+            const float2 r23 = fsub2(v23, make_float2(__uint_as_float(u23 << 16), __uint_as_float(u23 & 0xffff0000u)));
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(r01.x, r01.y);
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(r23.x, r23.y);
             // relative to pass 0 the slot address differs by an XOR (swizzle + K-row: below the
             // ring's 1 KB alignment, so XOR on the address is exact) and an offset (K-atom / K-step)
             const uint32_t xo = G::pass_xor(ps);
@@ -543,17 +546,15 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
             sts_v2((st_hi ^ xo) + ko, u01, u23);
             sts_v2((st_hi ^ (xo ^ 32u)) + ko, *reinterpret_cast<const uint32_t*>(&l01),
                    *reinterpret_cast<const uint32_t*>(&l23));
-            bacc.x = fmaf(cb, y[ps].x, bacc.x);
-            bacc.y = fmaf(cb, y[ps].y, bacc.y);
-            bacc.z = fmaf(cb, y[ps].z, bacc.z);
-            bacc.w = fmaf(cb, y[ps].w, bacc.w);
+            bacc01 = ffma2(cb2, y01, bacc01);
+            bacc23 = ffma2(cb2, y23, bacc23);
           }
           // my last stage of this row: publish the partial rhs of my stages (before the stage's
           // `full` arrive: the MMA warp's "rhs complete" signal then covers it)
           if (st + P >= nst) {
             const int useq = useq_base + __popc(B.ne_mask & ((1u << i) - 1u));
             const int bslot = useq % kBSlots;
-            float4 v = bacc;
+            float4 v = make_float4(bacc01.x, bacc01.y, bacc23.x, bacc23.y);
 #pragma unroll
             for (int off = CPR; off < 32; off <<= 1) {
               v.x += __shfl_xor_sync(kFull, v.x, off);
@@ -563,7 +564,8 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
             }
             mbar_wait_id(&b_empty[bslot], (uint32_t)(((useq / kBSlots) & 1) ^ 1), 0);
             if (lane < CPR) *reinterpret_cast<float4*>(bpart + (bslot * P + pw) * KS + 4 * q) = v;
-            bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+            bacc01 = make_float2(0.f, 0.f);
+            bacc23 = make_float2(0.f, 0.f);
           }
           fence_proxy_async_smem();
           if (kArrive1) {

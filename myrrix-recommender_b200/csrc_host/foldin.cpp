@@ -244,6 +244,16 @@ int foldin_update_many(const foldin_handle* h, float* X, float* Y, const int32_t
   return FOLDIN_OK;
 }
 
+int foldin_export_solver(const foldin_handle* h, int32_t which, double* qrt, double* rdiag, int32_t* perm) {
+  if (!h || !qrt || !rdiag || !perm || (which != 0 && which != 1)) return FOLDIN_E_ARG;
+  if (!h->have[which]) return FOLDIN_E_NOT_READY;
+  const Rrqr& s = h->solver[which];
+  memcpy(qrt, s.qrt.data(), sizeof(double) * (size_t)h->k * h->k);
+  memcpy(rdiag, s.rdiag.data(), sizeof(double) * (size_t)h->k);
+  for (int i = 0; i < h->k; i++) perm[i] = s.perm[i];
+  return FOLDIN_OK;
+}
+
 int foldin_anonymous_user(const foldin_handle* h, const float* item_rows, const float* values, int32_t n,
                           float* out) {
   if (!h || !out || n < 0 || (n > 0 && !item_rows)) return FOLDIN_E_ARG;

@@ -265,6 +265,35 @@ class NativeALS:
                                       out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
 
+    # -- the live model between builds (fold-in on the resident rows) ----------------------------
+    def recompute_state(self, singularity_threshold=1.0e-5, learn_rate=1.0, xtx=True, yty=True):
+        """Generation.recomputeState: Gramians from the resident factors (GPU), the generation's
+        solvers (libmyrrix_foldin.so: infNorm guard, pivoted QR), a copy of their factors on the device.
+        Returns the host-side FoldIn (anonymous users, single solves)."""
+        from .foldin import FoldIn
+        fi = FoldIn(self.features, self.gramian("x") if xtx else None, self.gramian("y") if yty else None,
+                    singularity_threshold=singularity_threshold, learn_rate=learn_rate)
+        for which in (0, 1):
+            st = fi.export(which)
+            if st is None:
+                self.check(self.lib.als_set_fold_in_state(self.h, which, None, None, None, learn_rate))
+            else:
+                qrt, rdiag, perm = st
+                self.check(self.lib.als_set_fold_in_state(
+                    self.h, which, qrt.ctypes.data_as(C.POINTER(C.c_double)),
+                    rdiag.ctypes.data_as(C.POINTER(C.c_double)), perm.ctypes.data_as(C.POINTER(C.c_int32)),
+                    learn_rate))
+        return fi
+
+    def fold_in(self, users, items, values=None):
+        """ServerRecommender.updateFeatures for a stream of writes, in order, on the resident rows."""
+        u, pu = self._i32(users)
+        i, pi = self._i32(items)
+        v = None if values is None else np.ascontiguousarray(values, dtype=np.float32).reshape(-1)
+        if u.size != i.size or (v is not None and v.size != u.size):
+            raise ValueError("users / items / values differ in length")
+        self.check(self.lib.als_fold_in(self.h, pu, pi, None if v is None else _fp(v), u.size))
+
     # -- top-N scoring on the resident model (include/myrrix_als.h, csrc/topn.cuh) --------------
     @staticmethod
     def _i32(a):

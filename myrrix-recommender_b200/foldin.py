@@ -22,6 +22,7 @@ SYMBOLS = [
     ("foldin_solve", C.c_int, [_H, C.c_int32, _f32p, _f64p]),
     ("foldin_update_features", C.c_int, [_H, _f32p, _f32p, C.c_float]),
     ("foldin_update_many", C.c_int, [_H, _f32p, _f32p, _i32p, _i32p, _f32p, C.c_int64]),
+    ("foldin_export_solver", C.c_int, [_H, C.c_int32, _f64p, _f64p, _i32p]),
     ("foldin_anonymous_user", C.c_int, [_H, _f32p, _f32p, C.c_int32, _f32p]),
 ]
 _lib = None
@@ -132,6 +133,19 @@ class FoldIn:
         if rc != FOLDIN_OK:
             raise RuntimeError("foldin_anonymous_user failed (%d)" % rc)
         return out
+
+    def export(self, which):
+        """(qrt [k, k], rdiag [k], perm [k]) of solver `which` (0: X'X, 1: Y'Y), or None."""
+        qrt = np.empty((self.k, self.k), np.float64)
+        rdiag = np.empty(self.k, np.float64)
+        perm = np.empty(self.k, np.int32)
+        rc = self.lib.foldin_export_solver(self.h, which, qrt.ctypes.data_as(_f64p), rdiag.ctypes.data_as(_f64p),
+                                           perm.ctypes.data_as(_i32p))
+        if rc == FOLDIN_E_NOT_READY:
+            return None
+        if rc != FOLDIN_OK:
+            raise RuntimeError("foldin_export_solver failed (%d)" % rc)
+        return qrt, rdiag, perm
 
     def close(self):
         if self.h:

@@ -49,6 +49,14 @@ class Recommender:
         ex = [self._item_index[int(i)] for i in excludeItemIDs if int(i) in self._item_index]
         return self._out(*self.als.recommend(rows, howMany, considerKnownItems, ex))
 
+    def setPreference(self, userID, itemID, value=1.0):
+        """The model part of ServerRecommender.setPreference (:735-760) for a known user and item: the
+        write is folded into the resident rows (updateFeatures); new IDs wait for the next build."""
+        if int(userID) not in self._user_index or int(itemID) not in self._item_index:
+            return False
+        self.als.fold_in([self._user_index[int(userID)]], [self._item_index[int(itemID)]], [value])
+        return True
+
     def recommendToAnonymous(self, itemIDs, values=None, howMany=10):
         """buildAnonymousUserFeatures (ServerRecommender.java:561-608, host fold-in library), then
         the same scoring with the anonymous user's items filtered (:540-552)."""

@@ -111,3 +111,63 @@ def test_ill_conditioned_and_singular_reports():
     with pytest.raises(O.SingularMatrixError) as eo:
         O.solve(G, np.ones(k))
     assert e.value.apparent_rank == eo.value.apparent_rank == 3
+
+
+# ---- fold-in on the resident rows (csrc/foldin_dev.cuh) against the host library ------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [30, 64, 100])
+def test_device_fold_in_matches_the_host_library(k):
+    import myrrix_recommender_b200 as M
+    from oracle import topn_oracle as T
+    U, I = 1500, 900
+    with M.NativeALS(k, device=0) as als:
+        als.synth_interactions(U, I, 20, seed=11, neg_fraction=0.05)
+        als.synth_y0(seed=11)
+        als.iterate(3)
+        als.sync()
+        fi = als.recompute_state()                 # Gramians on the GPU, solvers on the host, copy on the device
+        Xh, Yh = als.get_x(), als.get_y()
+        X0 = Xh.copy()
+        rng = np.random.default_rng(k)
+        n = 400
+        users = rng.integers(0, 40, n).astype(np.int32)      # few rows: every write sees earlier ones
+        items = rng.integers(0, 25, n).astype(np.int32)
+        values = rng.choice(np.array([1, 2, 5, -1, -3, 0.5], np.float32), n)
+        fi.update_many(Xh, Yh, users, items, values)         # the host library, in order
+        als.fold_in(users, items, values)                    # the device, in order, on the resident rows
+        Xd, Yd = als.get_x(), als.get_y()
+        for A, B in ((Xd, Xh), (Yd, Yh)):
+            assert np.isfinite(A).all()
+            # same factorisation, sums reassociated across lanes: identical except on rounding boundaries
+            assert np.abs(A - B).max() <= 4e-7 * np.abs(B).max()
+            assert (A == B).mean() > 0.995
+        assert np.abs(Xd[:40] - X0[:40]).max() > 1e-4          # the writes did move the rows
+        # a write moves the score it is about, and queries see the updated rows at once
+        ptr, idx, _ = als.get_interactions()
+        got_i, got_v = als.recommend([int(users[0])], 10)
+        want_i, want_v = T.recommend(Yd, Xd, ptr, idx, [int(users[0])], 10)
+        assert np.array_equal(got_i, want_i) and np.array_equal(got_v, want_v)
+        # no write, no change; bad indices are rejected
+        als.fold_in([], [], [])
+        with pytest.raises(ValueError):
+            als.fold_in([U], [0], [1.0])
+
+
+@pytest.mark.gpu
+def test_device_fold_in_one_sided_and_unset_state():
+    import myrrix_recommender_b200 as M
+    from myrrix_recommender_b200.factorizer import ExecutionException
+    k = 16
+    with M.NativeALS(k, device=0) as als:
+        als.synth_interactions(300, 200, 10, seed=3)
+        als.synth_y0(seed=3)
+        als.iterate(2)
+        als.sync()
+        with pytest.raises(ExecutionException):
+            als.fold_in([0], [0], [1.0])                     # no solver state yet
+        fi = als.recompute_state(xtx=False)                  # model.solver.xtx.compute=false
+        Xh, Yh = als.get_x(), als.get_y()
+        fi.update_many(Xh, Yh, np.array([1, 2, 1], np.int32), np.array([5, 5, 6], np.int32), None)
+        als.fold_in([1, 2, 1], [5, 5, 6])
+        assert np.array_equal(als.get_y(), Yh)               # items untouched without the X'X solver
+        assert np.abs(als.get_x() - Xh).max() <= 4e-7 * np.abs(Xh).max()
