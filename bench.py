@@ -449,18 +449,35 @@ def main():
                                            C.cast(h_val.data_ptr(), C.POINTER(C.c_float))))
         als.close()
 
+        trace = os.environ.get("BENCH_E2E_TRACE") == "1"  # development: phases of the call, with syncs
+
         def one_call():
+            marks = [("start", time.perf_counter())]
+
+            def mark(name):
+                if trace:
+                    torch.cuda.synchronize()
+                    marks.append((name, time.perf_counter()))
             a = M.NativeALS(k, device=local_rank, kernel=kernel)
             a.set_stream(stream.cuda_stream)
+            mark("create")
             a.check(lib.als_set_interactions(a.h, U, I, C.cast(h_ptr.data_ptr(), C.POINTER(C.c_int64)),
                                              C.cast(h_idx.data_ptr(), C.POINTER(C.c_int32)),
                                              C.cast(h_val.data_ptr(), C.POINTER(C.c_float))))
             a.n_users, a.n_items = U, I
+            mark("set_interactions")
             a.check(lib.als_set_y(a.h, C.cast(h_y0.data_ptr(), C.POINTER(C.c_float))))
+            mark("set_y")
             a.iterate(args.steps)
+            mark("iterate")
             a.check(lib.als_get_x(a.h, C.cast(h_x.data_ptr(), C.POINTER(C.c_float))))
             a.check(lib.als_get_y(a.h, C.cast(h_y.data_ptr(), C.POINTER(C.c_float))))
+            mark("get_x, get_y")
             a.close()
+            mark("destroy")
+            if trace:
+                dbg("e2e phases: " + ", ".join("%s %.0f ms" % (n, (t1 - t0) * 1e3) for (_, t0), (n, t1)
+                                                in zip(marks[:-1], marks[1:])))
 
         one_call()  # warm-up (allocator, first-touch)
         torch.cuda.synchronize()

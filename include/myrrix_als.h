@@ -267,8 +267,8 @@ int als_fold_in(als_handle *h, const int32_t *users, const int32_t *items, const
  * consider_known_items == 0 removes the intersection of the known items (the users' rows of R)
  * of those users that have any (:396-425); `exclude` lists further items to skip (the tag IDs /
  * IDRescorer.isFiltered of the caller; the callbacks themselves stay in the host language).
- * out_items / out_values: how_many entries, *out_count of them valid.  1 <= how_many <= 256,
- * 1 <= n_users <= 32.  ALS_E_NONFINITE: "Bad recommendation value" (RecommendIterator.java:99). */
+ * out_items / out_values: how_many entries, *out_count of them valid.  1 <= how_many <= 128,
+ * 1 <= n_users <= 16.  ALS_E_NONFINITE: "Bad recommendation value" (RecommendIterator.java:99). */
 int als_recommend(als_handle *h, const int32_t *users, int32_t n_users, int32_t how_many,
                   int32_t consider_known_items, const int32_t *exclude, int32_t n_exclude,
                   int32_t *out_items, float *out_values, int32_t *out_count);

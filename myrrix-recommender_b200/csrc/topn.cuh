@@ -34,10 +34,13 @@ namespace topn {
 constexpr int kTile = 128;     // items per tile = threads per CTA
 constexpr int kThreads = 128;
 constexpr int kMaxQ = 4;       // queries per pass over Y
-constexpr int kMaxVec = 32;    // feature vectors per pass (all its queries together)
-constexpr int kCap = 512;      // candidate keys per query per CTA (power of two)
-constexpr int kMaxN = 256;     // largest howMany of the fused path (kCap - kTile >= kMaxN)
-constexpr int kStages = 2;
+constexpr int kMaxVec = 16;    // feature vectors per pass (all its queries together)
+constexpr int kCap = 256;      // candidate keys per query per CTA (power of two)
+constexpr int kMaxN = 128;     // largest howMany of the fused path (kCap - kTile >= kMaxN)
+// Three stages: two tile loads (32 KB each at k = 64) in flight per CTA while a third is scored --
+// with two stages the pass was bound by the latency of the one load in flight (85 us per query over
+// 1 M x 64 items; HBM time 40 us).  k = 64: 96 KB ring + 12 KB, two CTAs per SM.
+constexpr int kStages = 3;
 static_assert(kCap - kTile >= kMaxN, "a tile's insertions must fit after a prune");
 
 struct Params {
@@ -88,12 +91,12 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* a, int n, 
 // Keep the best `n` of the `*cnt` keys in buf (capacity kCap); raise *thr to the n-th best when
 // there are that many.  Called by the whole CTA; ends with a barrier.
 __device__ __forceinline__ void prune(unsigned long long* buf, int* cnt, unsigned long long* thr, int n,
-                                      int tid, unsigned long long* gthr) {
+                                      int tid, unsigned long long* gthr, int nthreads = kThreads, int cap = kCap) {
   const int c = *cnt;
   __syncthreads();
-  for (int i = c + tid; i < kCap; i += kThreads) buf[i] = 0ull;
+  for (int i = c + tid; i < cap; i += nthreads) buf[i] = 0ull;
   __syncthreads();
-  bitonic_sort_desc(buf, kCap, tid, kThreads);
+  bitonic_sort_desc(buf, cap, tid, nthreads);
   if (tid == 0) {
     const int kept = c < n ? c : n;
     *cnt = kept;
@@ -201,11 +204,20 @@ __global__ void __launch_bounds__(kThreads) topn_score_kernel(const __grid_const
     }
     __syncthreads();
 
+    // filter words of my item, one per query, fetched before the scoring so their latency hides
+    unsigned exw[kMaxQ];
+#pragma unroll
+    for (int q = 0; q < kMaxQ; q++)
+      exw[q] = (p.excl && valid && q < p.n_q) ? __ldg(p.excl + (long long)q * p.excl_words + (item >> 5)) : 0u;
     double qsum = 0.0;
     int cur_q = vqs[0];
     auto finish_query = [&](int q, double sum) {
       if (!valid) return;
-      if (p.excl && ((p.excl[(long long)q * p.excl_words + (item >> 5)] >> (item & 31)) & 1u)) return;
+      unsigned w = 0u;
+#pragma unroll
+      for (int j = 0; j < kMaxQ; j++)
+        if (j == q) w = exw[j];
+      if ((w >> (item & 31)) & 1u) return;
       const float r = (float)(sum / (double)nvq[q]);  // RecommendIterator.java:98
       if (!isfinite(r)) {
         *p.nonfinite = 1;
@@ -261,39 +273,54 @@ __global__ void __launch_bounds__(kThreads) topn_score_kernel(const __grid_const
   }
   // ---- this CTA's best keys of every query ---------------------------------------------------
   for (int q = 0; q < p.n_q; q++) {
-    prune(buf + q * kCap, &cnt[q], &thr[q], p.how_many, tid, nullptr);
+    prune(buf + q * kCap, &cnt[q], &thr[q], p.how_many, tid, p.gthr + q);
     unsigned long long* dst = p.cand + ((long long)q * gridDim.x + blockIdx.x) * p.how_many;
     for (int i = tid; i < p.how_many; i += kThreads) dst[i] = (i < cnt[q]) ? buf[q * kCap + i] : 0ull;
     __syncthreads();
   }
 }
 
-// One CTA per query: the best how_many of the per-CTA lists, in result order.
-__global__ void __launch_bounds__(kThreads) topn_merge_kernel(const unsigned long long* cand, int lists,
-                                                              int how_many, int* out_items, float* out_values,
-                                                              int* out_count) {
-  __shared__ unsigned long long buf[kCap];
+// One CTA per query: the best how_many of the per-CTA lists, in result order.  gthr[q] is by now the
+// largest of the CTAs' own how_many-th keys -- a lower bound of the result's last key -- so only the
+// few keys at or above it are collected and sorted; every thread keeps kMergeLoads independent
+// loads of the (L2-resident) lists in flight.
+constexpr int kMergeThreads = 256;
+constexpr int kMergeLoads = 4;
+constexpr int kMergeCap = 2048;  // power of two
+static_assert(kMergeThreads * kMergeLoads <= kMergeCap - kMaxN, "a round's insertions must fit after a prune");
+__global__ void __launch_bounds__(kMergeThreads) topn_merge_kernel(const unsigned long long* cand, int lists,
+                                                                   const unsigned long long* gthr, int how_many,
+                                                                   int* out_items, float* out_values, int* out_count) {
+  __shared__ unsigned long long buf[kMergeCap];
   __shared__ unsigned long long thr;
   __shared__ int cnt;
   const int q = blockIdx.x, tid = threadIdx.x;
   if (tid == 0) {
-    thr = 0ull;
+    const unsigned long long g = gthr[q];
+    thr = g ? g - 1 : 0ull;  // key > thr  <=>  key >= g
     cnt = 0;
   }
   __syncthreads();
   const unsigned long long* src = cand + (long long)q * lists * how_many;
   const long long total = (long long)lists * how_many;
-  for (long long base = 0; base < total; base += kThreads) {
-    const long long i = base + tid;
-    if (i < total) {
-      const unsigned long long key = src[i];
-      if (key > thr) buf[atomicAdd(&cnt, 1)] = key;
+  constexpr int kRound = kMergeThreads * kMergeLoads;
+  for (long long base = 0; base < total; base += kRound) {
+    unsigned long long key[kMergeLoads];
+#pragma unroll
+    for (int j = 0; j < kMergeLoads; j++) {
+      const long long i = base + tid + (long long)j * kMergeThreads;
+      key[j] = i < total ? src[i] : 0ull;
     }
+#pragma unroll
+    for (int j = 0; j < kMergeLoads; j++)
+      if (key[j] > thr) buf[atomicAdd(&cnt, 1)] = key[j];
     __syncthreads();
-    if (cnt > kCap - kThreads) prune(buf, &cnt, &thr, how_many, tid, nullptr);
+    if (cnt > kMergeCap - kRound) prune(buf, &cnt, &thr, how_many, tid, nullptr, kMergeThreads, kMergeCap);
   }
-  prune(buf, &cnt, &thr, how_many, tid, nullptr);
-  for (int i = tid; i < how_many; i += kThreads) {
+  const int c = cnt;
+  const int cap = c <= 256 ? 256 : (c <= 512 ? 512 : (c <= 1024 ? 1024 : kMergeCap));  // sort no more than needed
+  prune(buf, &cnt, &thr, how_many, tid, nullptr, kMergeThreads, cap);
+  for (int i = tid; i < how_many; i += kMergeThreads) {
     const bool on = i < cnt;
     out_items[(long long)q * how_many + i] = on ? (int)(0xffffffffu - (unsigned)(buf[i] & 0xffffffffull)) : -1;
     out_values[(long long)q * how_many + i] = on ? from_ordered_bits((unsigned)(buf[i] >> 32)) : 0.f;

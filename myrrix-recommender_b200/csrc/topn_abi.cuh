@@ -90,8 +90,8 @@ int topn_launch_t(als_handle* h, TopNState* t, const topn::Params& p, int slot) 
   if (grid > t->grid) return fail(h, ALS_E_STATE, "top-N candidate buffer sized for %d CTAs", t->grid);
   kern<<<(int)grid, topn::kThreads, S::kTotal, h->stream>>>(t->map, p);
   CU(h, cudaGetLastError());
-  topn::topn_merge_kernel<<<p.n_q, topn::kThreads, 0, h->stream>>>(p.cand, (int)grid, p.how_many, t->out_items,
-                                                                    t->out_values, t->out_counts);
+  topn::topn_merge_kernel<<<p.n_q, topn::kMergeThreads, 0, h->stream>>>(p.cand, (int)grid, p.gthr, p.how_many,
+                                                                        t->out_items, t->out_values, t->out_counts);
   CU(h, cudaGetLastError());
   h->launches += 2;
   return ALS_OK;
