@@ -78,7 +78,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -87,9 +87,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None, t_load=None):
+        """Samples received inside the timed region [t0, t1]; when the region is shorter than the
+        sampling period, the samples of the warm-up + timed region [t_load, t1] (the same kernels,
+        back to back), and `window` says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -97,8 +100,13 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        window = "timed region"
+        rows = [r for t, r in self.rows if t0 is None or t0 <= t <= t1 + 0.02]
+        if not rows and t_load is not None:
+            rows = [r for t, r in self.rows if t_load + 0.05 <= t <= t1 + 0.05]
+            window = "warm-up + timed region (the timed region is shorter than the sampling period)"
         sm, mx, power, reasons = [], [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
                 for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6),
@@ -110,7 +118,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons),
+                "window": window}
 
 
 # --------------------------------------------------------------------------------------
@@ -356,23 +365,27 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing: W warm-up + exactly K timed iterations -----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # (nvidia-smi needs a few hundred ms before its first sample)
+        time.sleep(0.5)
+    t_load = time.perf_counter()
     als.iterate(args.warmup)
     als.sync()
     dbg("warm-up done")
     als.profile(True)
     als.timings(reset=True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
     ev0.record(stream)
     als.iterate(args.steps)
     ev1.record(stream)
     barrier()
+    t_end = time.perf_counter()
     dbg("timed region done")
     als.sync()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end, t_load) if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
     tm = als.timings(reset=True)
     als.profile(False)
