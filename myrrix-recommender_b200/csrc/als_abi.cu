@@ -81,11 +81,17 @@ struct Csr {
   long long row_begin = 0;   // global index of local row 0
 };
 
+#include <cuda.h>  // CUtensorMap
+
 struct TopNState;  // topn_abi.cuh
 
 struct als_handle {
   als_config cfg;
   TopNState* topn = nullptr;  // top-N scoring scratch, created on first use
+  // TMA tensor maps of the factor matrices for the row update's gathers ([rows][ks] fp32, one box = one row)
+  CUtensorMap gather_map[2];
+  const float* gather_map_base[2] = {nullptr, nullptr};
+  long long gather_map_rows[2] = {0, 0};
   // fold-in solver state of the generation (als_set_fold_in_state): [0] X'X, [1] Y'Y
   double* fi_qrt[2] = {nullptr, nullptr};
   double* fi_rdiag[2] = {nullptr, nullptr};
@@ -553,12 +559,31 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
     // role mix by average row length unless MYRRIX_ALS_MIX forced one at als_create
     const bool long_rows = h->mix_override ? (h->mix_override == 4)
                                            : (R.rows > 0 && R.nnz / R.rows >= kLongRowEntries);
+    const int mi = which == 0 ? 1 : 0;  // the X half gathers rows of Y and vice versa
+    if ((h->ks == 64 || h->ks == 32) && !h->legacy_umma) {
+      const long long m_rows = which == 0 ? h->n_items : h->n_users;
+      if (h->gather_map_base[mi] != M || h->gather_map_rows[mi] != m_rows) {
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (!enc) { nvtxRangePop(); return fail(h, ALS_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver"); }
+        const cuuint64_t gdim[2] = {(cuuint64_t)h->ks, (cuuint64_t)m_rows};
+        const cuuint64_t gstr[1] = {(cuuint64_t)h->ks * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)h->ks, 1};  // tile::gather4 takes four one-row boxes
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult cr = enc(&h->gather_map[mi], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)M, gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { nvtxRangePop(); return fail(h, ALS_E_CUDA, "cuTensorMapEncodeTiled(factor) failed (%d)", (int)cr); }
+        h->gather_map_base[mi] = M;
+        h->gather_map_rows[mi] = m_rows;
+      }
+    }
+    const CUtensorMap& tm = h->gather_map[mi];
     if (h->ks == 64 && !h->legacy_umma) {
-      rc = long_rows ? launch_row_update_v2_t<64, v2::MixLong>(p, h->sm_count, h->stream, h->err, sizeof(h->err))
-                     : launch_row_update_v2_t<64, v2::MixShort>(p, h->sm_count, h->stream, h->err, sizeof(h->err));
+      rc = long_rows ? launch_row_update_v2_t<64, v2::MixLong>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err))
+                     : launch_row_update_v2_t<64, v2::MixShort>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err));
     } else if (h->ks == 32 && !h->legacy_umma) {
-      rc = long_rows ? launch_row_update_v2_t<32, v2::Mixes<32>::Long>(p, h->sm_count, h->stream, h->err, sizeof(h->err))
-                     : launch_row_update_v2_t<32, v2::Mixes<32>::Short>(p, h->sm_count, h->stream, h->err, sizeof(h->err));
+      rc = long_rows ? launch_row_update_v2_t<32, v2::Mixes<32>::Long>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err))
+                     : launch_row_update_v2_t<32, v2::Mixes<32>::Short>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err));
     } else {
       rc = launch_row_update_umma(h->ks, p, long_rows, h->sm_count, h->stream, h->err, sizeof(h->err));
     }

@@ -38,6 +38,8 @@
 //   Cholesky    chol_blocked.cuh: 16-column panels on the CUDA cores, trailing updates as
 //               3xTF32 mma.sync on fragments of the slot, in place.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only)
+
 #include "chol_blocked.cuh"
 #include "common.cuh"
 #include "row_update_simt.cuh"  // RowUpdateParams
@@ -80,6 +82,25 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef ALS_V2_XSLOTS
 #define ALS_V2_XSLOTS 0
 #endif
+
+// 1: the asynchronous gathers are TMA tile::gather4 loads (cp.async.bulk.tensor.2d ... tile::gather4: four
+// factor rows per instruction, written into the ring slot by the TMA engine, bytes counted on the slot's
+// mbarrier; indices beyond a row's last entry point past the tensor and are zero-filled);
+// 0: Ampere-style cp.async (LDGSTS) copies, 16 bytes per lane
+#ifndef ALS_V2_GATHER4
+#define ALS_V2_GATHER4 1
+#endif
+constexpr bool kGather4 = ALS_V2_GATHER4 != 0;
+constexpr int kOobRow = 0x40000000;  // a row index beyond any factor matrix: TMA fills zeros
+
+// four rows {r0..r3} of the tensor (one box row each: KS floats from column 0) -> dst .. dst + 4 * KS * 4
+__device__ __forceinline__ void tma_gather4(uint32_t dst_saddr, const CUtensorMap* map, int r0, int r1, int r2, int r3,
+                                            uint32_t mbar_saddr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst_saddr), "l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(mbar_saddr)
+      : "memory");
+}
 
 // extra own-stages of look-ahead for a producer's index / value loads (see the producer loop)
 #ifndef ALS_V2_FETCH_EXTRA
@@ -337,7 +358,8 @@ __device__ __forceinline__ void load_batch(const RowUpdateParams& p, long long r
 }
 
 template <int KS, class MX>
-__global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const RowUpdateParams p) {
+__global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const RowUpdateParams p,
+                                                                        const __grid_constant__ CUtensorMap tmapM) {
   static_assert(KS == 64 || KS == 32, "second-generation kernel: k = 32 or 64");
   static_assert(KS == 64 || MX::kAsync, "register-gather producers are kept for k = 64 A/B builds only");
   using G = Geom<KS>;
@@ -379,7 +401,9 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
     for (int i = 0; i < kStages; i++) {
       mbar_init(&full[i], kArrive1 ? 1 : 32);  // the producer warp that owns the stage (every lane, or one elected)
       mbar_init(&empty[i], 1);
-      mbar_init(&raw_full[i], 32);  // copy-completion arrivals of the 32 lanes that gathered the stage
+      // gathered bytes of the stage: TMA transaction bytes behind one arrival, or the copy-completion
+      // arrivals of the 32 lanes that gathered it
+      mbar_init(&raw_full[i], (kGather4 && MX::kAsync) ? 1 : 32);
     }
     for (int i = 0; i < kAccSlots; i++) {
       mbar_init(&acc_full[i], 1);
@@ -468,6 +492,19 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
       // entries sub, sub + RPP, ...; the slot's mbarrier gets this lane's arrival when they land
       auto issue = [&](int my_idx, uint32_t gs, uint32_t gp) {
         mbar_wait_id(&empty[gs], gp ^ 1u, 1);  // the MMA has read the slot's previous stage
+        if constexpr (kGather4) {
+          // lane e (< E) holds the index of entry e: every fourth lane gathers entries e .. e + 3 with one
+          // TMA instruction (rows land at entry * KS * 4, exactly where the 16-byte copies put them)
+          const int i0 = my_idx < 0 ? kOobRow : my_idx;
+          const int i1 = __shfl_down_sync(kFull, i0, 1);
+          const int i2 = __shfl_down_sync(kFull, i0, 2);
+          const int i3 = __shfl_down_sync(kFull, i0, 3);
+          const uint32_t bar = smem_u32(&raw_full[gs]);
+          if (lane == 0) mbar_arrive_expect_tx(&raw_full[gs], (uint32_t)G::kBytes);
+          if (lane < E && (lane & 3) == 0)
+            tma_gather4(ring_a + gs * (uint32_t)G::kBytes + (uint32_t)(lane * (KS * 4)), &tmapM, i0, i1, i2, i3, bar);
+          return;
+        }
         const uint32_t dst = ring_a + gs * (uint32_t)G::kBytes + (uint32_t)(sub * (KS * 4) + q * 16);
 #pragma unroll
         for (int ps = 0; ps < 8; ps++) {
@@ -967,12 +1004,12 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
 }  // namespace v2
 
 template <int KS, class MX>
-inline int launch_row_update_v2_t(const RowUpdateParams& p, int sm_count, cudaStream_t stream, char* err,
-                                  size_t err_len) {
+inline int launch_row_update_v2_t(const RowUpdateParams& p, const CUtensorMap& tmapM, int sm_count, cudaStream_t stream,
+                                  char* err, size_t err_len) {
   using S = v2::Smem<KS, MX>;
   long long grid = sm_count;
   if (grid > p.n_rows) grid = p.n_rows > 0 ? p.n_rows : 1;
-  v2::row_update_v2_kernel<KS, MX><<<(int)grid, MX::kThreads, S::kTotal, stream>>>(p);
+  v2::row_update_v2_kernel<KS, MX><<<(int)grid, MX::kThreads, S::kTotal, stream>>>(p, tmapM);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, err_len, "row_update_v2 launch: %s", cudaGetErrorString(e));
