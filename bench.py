@@ -34,12 +34,17 @@ CONFIGS = {
     # c3 at 1/5 scale (same entries per user and per item): profiling-only, ncu replays need
     # the working set small enough to save/restore between passes
     "c3p": dict(users=2_000_000, items=200_000, nnz_per_user=100, k=64),
+    # power-law data in the shape of config 5 (50M x 5M, ~200/user, power-law, k=128, 8 GPUs) at 1/25 scale
+    # on one GPU and at k=64 (the tensor-core path; k=128 runs on the CUDA-core kernel): rows from 20 to
+    # 20 000 entries, a few items that nearly every user has.  Device-resident line only (no CPU arm).
+    "c5p": dict(users=2_000_000, items=200_000, nnz_per_user=200, k=64, powerlaw=True, max_nnz=20_000),
 }
 WORKLOAD_NAMES = {
     "c1": "10k x 2k, 20 nnz/user, k=16",
     "c2": "1M x 100k, 50 nnz/user, k=32",
     "c3": "10M x 1M, 100 nnz/user, k=64 (headline)",
     "c3p": "2M x 200k, 100 nnz/user, k=64 (1/5-scale headline, profiling only)",
+    "c5p": "2M x 200k, ~200 nnz/user power-law (max 20000), Zipf items, k=64 (config 5 at 1/25 scale, one GPU)",
 }
 
 
@@ -263,7 +268,7 @@ def sampled_parity(als, cfg, rank, world, n_user_rows=200, n_item_rows=50):
     def rows_csr(rows_local, by_column):
         ptrs, idxs, vals = [0], [], []
         for r in rows_local:
-            _, i, v = als.get_interaction_rows(int(r), 1, by_column=by_column, capacity=1 << 20)
+            _, i, v = als.get_interaction_rows(int(r), 1, by_column=by_column, capacity=max(1 << 20, U + 1))
             idxs.append(i); vals.append(v); ptrs.append(ptrs[-1] + i.size)
         return np.array(ptrs, np.int64), np.concatenate(idxs), np.concatenate(vals)
 
@@ -347,7 +352,14 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         als.comm_init(rank, world, uid[0])
     dbg("comm ready, synthesising")
-    als.synth_interactions(U, I, nnz_pu, seed=SEED, neg_fraction=0.0)
+    if cfg.get("powerlaw"):
+        if world > 1:
+            raise SystemExit("the power-law generator fills single-GPU handles (config c5p: --gpus 1)")
+        args.no_e2e = args.no_cpu_baseline = True
+        als.synth_interactions_powerlaw(U, I, nnz_pu, max_nnz=cfg["max_nnz"], seed=SEED, neg_fraction=0.0)
+        nnz = int(als.info().nnz)
+    else:
+        als.synth_interactions(U, I, nnz_pu, seed=SEED, neg_fraction=0.0)
     als.synth_y0(seed=SEED)
     dbg("workload resident")
     h_y0 = None

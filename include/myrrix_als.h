@@ -213,6 +213,12 @@ int als_get_timings(als_handle *h, als_timings *out, int32_t reset);
  * orientations) without touching the host. */
 int als_synth_interactions(als_handle *h, int64_t n_users, int64_t n_items, int32_t nnz_per_user,
                            uint64_t seed, double neg_fraction);
+/* Power-law variant: entries per user from a truncated power law (density
+ * ~ x^-2 on [1, max_nnz], scaled to a mean of about mean_nnz, at least one), item popularity
+ * Zipf(s = 1) over a pseudo-random permutation of the items, no item twice per user; strengths as
+ * above.  Single-GPU handles only. */
+int als_synth_interactions_powerlaw(als_handle *h, int64_t n_users, int64_t n_items, double mean_nnz,
+                                    int32_t max_nnz, uint64_t seed, double neg_fraction);
 /* Y0: every row k i.i.d. N(0,1) normalised to unit L2 norm in fp32 (the distribution of
  * RandomUtils.doRandomUnitVector, common/.../random/RandomUtils.java:88-100). */
 int als_synth_y0(als_handle *h, uint64_t seed);

@@ -72,6 +72,8 @@ SYMBOLS = [
     ("als_get_timings", C.c_int, [_H, C.POINTER(AlsTimings), C.c_int32]),
     ("als_synth_interactions", C.c_int, [_H, C.c_int64, C.c_int64, C.c_int32, C.c_uint64,
                                          C.c_double]),
+    ("als_synth_interactions_powerlaw", C.c_int, [_H, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.c_uint64,
+                                                  C.c_double]),
     ("als_synth_y0", C.c_int, [_H, C.c_uint64]),
     ("als_get_interactions", C.c_int, [_H, _i64p, _i32p, _f32p]),
     ("als_get_interactions_by_column", C.c_int, [_H, _i64p, _i32p, _f32p]),

@@ -92,6 +92,11 @@ struct als_handle {
   CUtensorMap gather_map[2];
   const float* gather_map_base[2] = {nullptr, nullptr};
   long long gather_map_rows[2] = {0, 0};
+  // visiting order of the row updates per orientation (rows by length, longest first), built lazily;
+  // invalidated whenever an interaction array is replaced (free_csr)
+  int* d_order[2] = {nullptr, nullptr};
+  long long order_rows[2] = {0, 0};
+  bool order_valid[2] = {false, false};
   // fold-in solver state of the generation (als_set_fold_in_state): [0] X'X, [1] Y'Y
   double* fi_qrt[2] = {nullptr, nullptr};
   double* fi_rdiag[2] = {nullptr, nullptr};
@@ -127,6 +132,7 @@ struct als_handle {
   int simt_blocks_per_sm = 1;
   int mix_override = 0;   // MYRRIX_ALS_MIX=4|8, read once at als_create
   bool legacy_umma = false;  // MYRRIX_ALS_V1=1: round-1 tensor-core kernel (A/B runs)
+  bool no_row_order = false; // MYRRIX_ALS_NO_ROW_ORDER=1: visit rows as stored (A/B runs)
   // probe scratch (grown on demand, freed with the handle)
   int* d_probe_idx = nullptr;
   double* d_probe_out = nullptr;
@@ -236,6 +242,7 @@ void dev_free_ipc(als_handle* h, T** p, size_t count) {
 }
 
 void free_csr(als_handle* h, Csr* c) {
+  h->order_valid[0] = h->order_valid[1] = false;
   dev_free(h, &c->ptr, (size_t)c->rows + 1);
   dev_free(h, &c->idx, (size_t)c->nnz);
   dev_free(h, &c->val, (size_t)c->nnz);
@@ -510,6 +517,42 @@ int configure_kernels(als_handle* h) {
   return ALS_OK;
 }
 
+// rows of R by length, longest first (stable: equal lengths keep their stored order, so uniform
+// workloads are visited exactly as before)
+int ensure_row_order(als_handle* h, const Csr& R, int which) {
+  if (h->order_valid[which] && h->order_rows[which] == R.rows) return ALS_OK;
+  if (R.rows >= (1LL << 31)) return fail(h, ALS_E_UNSUPPORTED, "more than 2^31 - 1 local rows");
+  dev_free(h, &h->d_order[which], (size_t)h->order_rows[which]);
+  h->order_rows[which] = 0;
+  h->order_valid[which] = false;
+  const size_t n = (size_t)R.rows;
+  int rc;
+  unsigned *k_in = nullptr, *k_out = nullptr;
+  int* v_in = nullptr;
+  if ((rc = dev_alloc(h, &h->d_order[which], n)) != ALS_OK) return rc;
+  h->order_rows[which] = R.rows;
+  if ((rc = dev_alloc(h, &k_in, n)) != ALS_OK || (rc = dev_alloc(h, &k_out, n)) != ALS_OK ||
+      (rc = dev_alloc(h, &v_in, n)) != ALS_OK) {
+    dev_free(h, &k_in, n); dev_free(h, &k_out, n); dev_free(h, &v_in, n);
+    return rc;
+  }
+  row_length_keys_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(R.ptr, R.rows, k_in, v_in);
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, k_in, k_out, v_in, h->d_order[which],
+                                                            (int)n, 0, 32, h->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, h->stream);
+  if (e == cudaSuccess)
+    e = cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, k_in, k_out, v_in, h->d_order[which], (int)n, 0, 32,
+                                                  h->stream);
+  if (tmp) cudaFreeAsync(tmp, h->stream);
+  dev_free(h, &k_in, n); dev_free(h, &k_out, n); dev_free(h, &v_in, n);
+  h->launches += 2;
+  if (e != cudaSuccess) return fail(h, ALS_E_CUDA, "row order sort: %s", cudaGetErrorString(e));
+  h->order_valid[which] = true;
+  return ALS_OK;
+}
+
 int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, int which) {
   RowUpdateParams p;
   p.row_ptr = R.ptr;
@@ -531,6 +574,12 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
   p.ticket = h->d_ticket;
   p.row_list = nullptr;
   p.row_list_count = nullptr;
+  p.row_order = nullptr;
+  if (!h->no_row_order && R.rows > 0) {
+    const int orc = ensure_row_order(h, R, which);
+    if (orc != ALS_OK) return orc;
+    p.row_order = h->d_order[which];
+  }
   p.solve_empty = 0;
   p.retry_rows = nullptr;
   p.retry_count = nullptr;
@@ -1014,6 +1063,7 @@ int als_create(const als_config* cfg, als_handle** out) {
   }
   if (const char* e = getenv("MYRRIX_ALS_V1")) h->legacy_umma = atoi(e) != 0;
   if (const char* e = getenv("MYRRIX_ALS_NO_P2P")) h->p2p_disabled = atoi(e) != 0;
+  if (const char* e = getenv("MYRRIX_ALS_NO_ROW_ORDER")) h->no_row_order = atoi(e) != 0;
   CU(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   {
@@ -1063,6 +1113,7 @@ int als_destroy(als_handle* h) {
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   topn_free(h);
   for (int w = 0; w < 2; w++) { cudaFree(h->fi_qrt[w]); cudaFree(h->fi_rdiag[w]); cudaFree(h->fi_perm[w]); }
+  for (int w = 0; w < 2; w++) dev_free(h, &h->d_order[w], (size_t)h->order_rows[w]);
   free_csr(h, &h->by_user);
   free_csr(h, &h->by_item);
   cudaFree(h->X); cudaFree(h->Y);  // (cudaIpc-mappable: plain allocations)
@@ -1605,6 +1656,57 @@ int als_synth_interactions(als_handle* h, int64_t n_users, int64_t n_items, int3
   if (rc != ALS_OK) return rc;
   h->have_by_item = true;
   return ALS_OK;
+}
+
+static unsigned long long gcd_u64(unsigned long long a, unsigned long long b) {
+  while (b) { const unsigned long long t = a % b; a = b; b = t; }
+  return a;
+}
+
+int als_synth_interactions_powerlaw(als_handle* h, int64_t n_users, int64_t n_items, double mean_nnz,
+                                    int32_t max_nnz, uint64_t seed, double neg_fraction) {
+  if (!h) return ALS_E_ARG;
+  if (!(mean_nnz >= 1.0) || max_nnz < 2 || n_items < 1) return fail(h, ALS_E_ARG, "bad power-law parameters");
+  if (neg_fraction < 0.0 || neg_fraction > 1.0) return fail(h, ALS_E_ARG, "bad neg_fraction");
+  if (h->world > 1) return fail(h, ALS_E_UNSUPPORTED, "the power-law generator fills single-GPU handles");
+  CU(h, cudaSetDevice(h->device));
+  int rc = set_dims(h, n_users, n_items);
+  if (rc != ALS_OK) return rc;
+  Csr& A = h->by_user;
+  free_csr(h, &A);
+  h->have_by_item = false;
+  if ((rc = reset_for_new_interactions(h)) != ALS_OK) return rc;
+  // E[x] of the truncated law = ln(n_max) n_max / (n_max - 1): scale the draw so the mean is mean_nnz
+  const double ex = log((double)max_nnz) * (double)max_nnz / ((double)max_nnz - 1.0);
+  const double scale = mean_nnz / ex;
+  unsigned long long mul = (mix64(seed ^ 0x2545f4914f6cdd1dULL) % (unsigned long long)n_items) | 1ULL;
+  while (gcd_u64(mul, (unsigned long long)n_items) != 1ULL) mul += 2ULL;
+  const unsigned long long add = mix64(seed ^ 0x9e3779b97f4a7c15ULL) % (unsigned long long)n_items;
+  A.rows = n_users;
+  A.row_begin = 0;
+  long long* counts = nullptr;
+  if ((rc = dev_alloc(h, &counts, (size_t)n_users + 1)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &A.ptr, (size_t)n_users + 1)) != ALS_OK) return rc;
+  powerlaw_counts_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(0, n_users, n_items, scale, max_nnz, seed, counts);
+  {
+    void* stmp = nullptr;
+    size_t sbytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, sbytes, counts, A.ptr, (int)(n_users + 1), h->stream);
+    CU(h, cudaMalloc(&stmp, sbytes ? sbytes : 1));
+    cub::DeviceScan::ExclusiveSum(stmp, sbytes, counts, A.ptr, (int)(n_users + 1), h->stream);
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(stmp);
+  }
+  dev_free(h, &counts, (size_t)n_users + 1);
+  CU(h, cudaMemcpy(&A.nnz, A.ptr + n_users, sizeof(long long), cudaMemcpyDeviceToHost));
+  if ((rc = dev_alloc(h, &A.idx, (size_t)A.nnz)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &A.val, (size_t)A.nnz)) != ALS_OK) return rc;
+  const unsigned int thr = (unsigned int)(neg_fraction * 16777216.0);
+  powerlaw_rows_kernel<<<h->sm_count * 8, 128, 0, h->stream>>>(0, n_users, n_items, seed, thr, mul, add, A.ptr, A.idx,
+                                                                A.val);
+  h->launches += 3;
+  CU(h, cudaGetLastError());
+  return build_transpose(h);
 }
 
 int als_synth_y0(als_handle* h, uint64_t seed) {

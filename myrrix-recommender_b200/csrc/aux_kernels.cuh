@@ -101,6 +101,17 @@ __global__ void stop_rule_kernel(const double* __restrict__ fresh, double* __res
   out[1] = total_weight;
 }
 
+// keys[r] = entries of row r, vals[r] = r: sorted by key, descending, they give the visiting order of
+// the row updates (longest rows first)
+__global__ void row_length_keys_kernel(const long long* __restrict__ ptr, long long n_rows, unsigned* __restrict__ keys,
+                                       int* __restrict__ vals) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+    keys[r] = (unsigned)(ptr[r + 1] - ptr[r]);
+    vals[r] = (int)r;
+  }
+}
+
 // out[i][0..k) = F[rows[i]][0..k): selected factor rows, unpadded (als_get_rows)
 __global__ void gather_rows_kernel(const float* __restrict__ F, int ks, int k, const int* __restrict__ rows,
                                    int n, float* __restrict__ out) {
@@ -183,6 +194,62 @@ __global__ void synth_item_block_kernel(long long n_users, long long n_items, in
       n++;
     }
     if (counts) counts[u] = n;
+  }
+}
+
+// ---- power-law workload ---------------------------------------------
+// Per-user entry counts from a truncated power law (density ~ x^-2 on [1, n_max], scaled so the mean
+// is ~mean_nnz), item popularity Zipf(s = 1) over a pseudo-random permutation of the items, no item
+// twice per user.  Counter-based like the uniform generator: everything is a function of
+// (seed, user, j); a numpy twin in the test infrastructure mirrors it.
+__host__ __device__ inline double synth_unit(unsigned long long h) {  // (0, 1), 53 bits
+  return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+// entries of user u: clamp(round(scale / (1 - U (1 - 1/n_max))), 1, min(n_max, n_items))
+__host__ __device__ inline long long powerlaw_count(unsigned long long seed, unsigned long long user, double scale,
+                                                    int n_max, long long n_items) {
+  const double u = synth_unit(synth_hash(seed ^ 0x7c3a9f1d5b2e8461ULL, user, 0ULL));
+  const double x = 1.0 / (1.0 - u * (1.0 - 1.0 / (double)n_max));  // inverse CDF, x in [1, n_max)
+  long long n = (long long)(scale * x + 0.5);
+  if (n < 1) n = 1;
+  if (n > n_max) n = n_max;
+  if (n > n_items) n = n_items;
+  return n;
+}
+__global__ void powerlaw_counts_kernel(long long row_begin, long long n_local_rows, long long n_items, double scale,
+                                       int n_max, unsigned long long seed, long long* __restrict__ counts) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r <= n_local_rows; r += stride)
+    counts[r] = r < n_local_rows ? powerlaw_count(seed, (unsigned long long)(row_begin + r), scale, n_max, n_items) : 0;
+}
+// Entries of each user (one thread per user: the distinctness fix-up is a running maximum).
+// Draw j of n comes from stratum j of the Zipf CDF: rank = floor((n_items + 1)^((j + U_j) / n)) - 1,
+// made strictly increasing (rank_j = max(rank_j, rank_{j-1} + 1)) and kept below n_items - (n - 1 - j);
+// item = (mul * rank + add) mod n_items with gcd(mul, n_items) = 1.
+__global__ void powerlaw_rows_kernel(long long row_begin, long long n_local_rows, long long n_items,
+                                     unsigned long long seed, unsigned int neg_threshold_24,
+                                     unsigned long long perm_mul, unsigned long long perm_add,
+                                     const long long* __restrict__ row_ptr, int* __restrict__ col_idx,
+                                     float* __restrict__ val) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const double log_n = log1p((double)n_items);
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_local_rows; r += stride) {
+    const long long e0 = row_ptr[r], n = row_ptr[r + 1] - e0;
+    const unsigned long long user = (unsigned long long)(row_begin + r);
+    long long prev = -1;
+    for (long long j = 0; j < n; j++) {
+      const unsigned long long h = synth_hash(seed, user, (unsigned long long)j);
+      const double v = ((double)j + synth_unit(h)) / (double)n;
+      long long rank = (long long)floor(expm1(v * log_n));
+      if (rank <= prev) rank = prev + 1;
+      const long long cap = n_items - (n - j);  // leaves room for the entries still to come
+      if (rank > cap) rank = cap;
+      prev = rank;
+      col_idx[e0 + j] = (int)((perm_mul * (unsigned long long)rank + perm_add) % (unsigned long long)n_items);
+      float s = (float)(1 + (int)((h & 0xffffULL) % 5ULL));
+      if (((h >> 8) & 0xffffffULL) < neg_threshold_24) s = -s;
+      val[e0 + j] = s;
+    }
   }
 }
 

@@ -46,6 +46,10 @@ struct RowUpdateParams {
   // Row-list mode (CUDA-core kernel): process only row_list[0 .. *row_list_count).
   const int* row_list;
   const int* row_list_count;
+  // Visiting order of the rows (a permutation of [0, n_rows), longest rows first; nullptr: as stored):
+  // with skewed row lengths (power-law data) the long rows must start first, or the CTA that meets
+  // one last decides the kernel's tail.
+  const int* row_order;
   // Solve rows without entries too (W_u = G, b_u = 0): set for the list of rows that are keys
   // of the reference's map but whose entries were all pruned (InputFilesReader.java:202-211).
   int solve_empty;
@@ -122,6 +126,8 @@ row_update_simt_kernel(const RowUpdateParams p) {
       row = p.row_list[row];
     } else if (row >= p.n_rows) {
       break;
+    } else if (p.row_order) {
+      row = p.row_order[row];
     }
     const long long e0 = p.row_ptr[row], e1 = p.row_ptr[row + 1];
     const long long nu = e1 - e0;

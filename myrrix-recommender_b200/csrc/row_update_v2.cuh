@@ -339,8 +339,9 @@ __device__ __forceinline__ void load_batch(const RowUpdateParams& p, long long r
                                            int lane, uint32_t base, RowBatch& B) {
   B.e0 = 0;
   B.cnt = 0;
-  const long long myrow = rb + lane * row_step;
-  if (myrow < p.n_rows) {
+  const long long mypos = rb + lane * row_step;  // position in the visiting order
+  if (mypos < p.n_rows) {
+    const long long myrow = p.row_order ? (long long)p.row_order[mypos] : mypos;
     B.e0 = p.row_ptr[myrow];
     B.cnt = (int)(p.row_ptr[myrow + 1] - B.e0);
   }
@@ -759,13 +760,17 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
     uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty), dlo = (uint32_t)desc0;
     uint32_t gseg = 0;
     uint32_t useq = 0;
-    long long row = blockIdx.x;
+    long long row = blockIdx.x;  // position in the visiting order
+    auto count_at = [&](long long pos) {
+      const long long r = p.row_order ? (long long)__ldg(p.row_order + pos) : pos;
+      return (int)(__ldg(p.row_ptr + r + 1) - __ldg(p.row_ptr + r));
+    };
     int cnt_next = 0;
-    if (row < p.n_rows) cnt_next = (int)(__ldg(p.row_ptr + row + 1) - __ldg(p.row_ptr + row));
+    if (row < p.n_rows) cnt_next = count_at(row);
     for (; row < p.n_rows; row += row_step) {
       const int cnt = cnt_next;
       const long long nrow = row + row_step;
-      if (nrow < p.n_rows) cnt_next = (int)(__ldg(p.row_ptr + nrow + 1) - __ldg(p.row_ptr + nrow));
+      if (nrow < p.n_rows) cnt_next = count_at(nrow);
       if (cnt == 0) continue;
       const int nst = (cnt + E - 1) / E;
       for (int st0 = 0; st0 < nst; st0 += kSegStages, gseg++) {
@@ -820,8 +825,11 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
     for (long long rb = blockIdx.x; rb < p.n_rows; rb += 32 * row_step) {
       int cnt_l = 0;
       {
-        const long long myrow = rb + lane * row_step;
-        if (myrow < p.n_rows) cnt_l = (int)(p.row_ptr[myrow + 1] - p.row_ptr[myrow]);
+        const long long mypos = rb + lane * row_step;
+        if (mypos < p.n_rows) {
+          const long long myrow = p.row_order ? (long long)p.row_order[mypos] : mypos;
+          cnt_l = (int)(p.row_ptr[myrow + 1] - p.row_ptr[myrow]);
+        }
       }
       const long long left = (p.n_rows - rb + row_step - 1) / row_step;
       const int nb = left < 32 ? (int)left : 32;
@@ -914,7 +922,8 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
         const int cnt = __shfl_sync(kFull, B.cnt, ib);
         if (cnt == 0) continue;
         if (useq % kCholWarps != cw) { useq++; continue; }
-        const long long row = rb + ib * row_step;
+        const long long pos = rb + ib * row_step;
+        const long long row = p.row_order ? (long long)__ldg(p.row_order + pos) : pos;
         const int nst = (cnt + E - 1) / E;
         const int smod = __shfl_sync(kFull, smod_l, ib);
         const int bs = useq % kBSlots;

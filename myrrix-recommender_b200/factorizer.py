@@ -170,6 +170,12 @@ class NativeALS:
                                                    neg_fraction))
         self.n_users, self.n_items = int(n_users), int(n_items)
 
+    def synth_interactions_powerlaw(self, n_users, n_items, mean_nnz, max_nnz=20000, seed=1234567890,
+                                    neg_fraction=0.0):
+        self.check(self.lib.als_synth_interactions_powerlaw(self.h, n_users, n_items, float(mean_nnz), int(max_nnz),
+                                                            seed, neg_fraction))
+        self.n_users, self.n_items = n_users, n_items
+
     def synth_y0(self, seed=1234567890):
         self.check(self.lib.als_synth_y0(self.h, seed))
 

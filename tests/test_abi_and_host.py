@@ -146,3 +146,26 @@ def test_synth_twin_properties():
     p2, i2, v2 = synth.synth_rows(0, 400, 1000, 20, seed=1234567890, neg_fraction=0.05)
     assert np.array_equal(i2[10 * 20:210 * 20], idx)  # counter-based: shard == slice of whole
     assert np.array_equal(v2[10 * 20:210 * 20], val)
+
+
+def test_powerlaw_twin_properties():
+    """The power-law workload of config 5: skewed row lengths, Zipf-like item popularity,
+    no item twice per user, counter-based (a shard is a slice of the whole)."""
+    from oracle import synth
+    ptr, idx, val = synth.synth_rows_powerlaw(0, 20000, 5000, 40, max_nnz=2000, neg_fraction=0.05)
+    n = np.diff(ptr)
+    assert n.min() >= 1 and n.max() <= 2000 and 30 < n.mean() < 50
+    assert n.max() > 20 * np.median(n)                     # a heavy tail of long rows
+    assert idx.min() >= 0 and idx.max() < 5000
+    for u in range(0, 20000, 61):
+        row = idx[ptr[u]:ptr[u + 1]]
+        assert len(set(row.tolist())) == row.size          # distinct items per user
+    pop = np.sort(np.bincount(idx, minlength=5000))[::-1]
+    assert pop[0] > 100 * np.median(pop)                   # a few very popular items
+    assert set(np.abs(val)) == {1, 2, 3, 4, 5} and 0.02 < (val < 0).mean() < 0.09
+    p2, i2, v2 = synth.synth_rows_powerlaw(100, 300, 5000, 40, max_nnz=2000, neg_fraction=0.05)
+    assert np.array_equal(i2, idx[ptr[100]:ptr[400]]) and np.array_equal(v2, val[ptr[100]:ptr[400]])
+    full = synth.synth_rows_powerlaw(0, 50, 30, 40, max_nnz=2000)  # rows as long as the item set
+    assert np.diff(full[0]).max() == 30
+    for u in range(50):
+        assert len(set(full[1][full[0][u]:full[0][u + 1]].tolist())) == full[0][u + 1] - full[0][u]

@@ -5,6 +5,8 @@ Tolerance (BASELINE.json north_star): factor matrices within 1e-4 relative of th
 reference arithmetic after a fixed iteration count, identical lambda/alpha/k/Y0:
   ||A-B||_F/||B||_F <= 1e-4  and  max|A-B|/max|B| <= 1e-4       
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -617,3 +619,29 @@ def test_device_stop_rule_equals_host_stop_rule(M, goldens):
         assert runs[0][0] == runs[1][0]
         assert runs[0][1] == runs[1][1]  # bit-identical statistic
         assert np.array_equal(runs[0][2], runs[1][2])
+
+
+@pytest.mark.gpu
+def test_powerlaw_generator_matches_its_twin_and_factors_match_the_oracle(M, O):
+    """Config-5-style data: the device generator against oracle/synth.py bit for bit, then
+    two iterations on it (rows from a handful to thousands of entries, a few items that nearly every
+    user has) against the oracle."""
+    from oracle import synth
+    U, I, k = 6000, 2500, 64
+    with M.NativeALS(k) as als:
+        als.synth_interactions_powerlaw(U, I, 30, max_nnz=2000, seed=77, neg_fraction=0.05)
+        ptr, idx, val = als.get_interactions()
+        tp, ti, tv = synth.synth_rows_powerlaw(0, U, I, 30, max_nnz=2000, seed=77, neg_fraction=0.05)
+        assert np.array_equal(ptr, tp) and np.array_equal(idx, ti) and np.array_equal(val, tv)
+        cp, ci, cv = als.get_interactions(by_column=True)
+        assert cp[-1] == ptr[-1] and np.diff(cp).max() > 0.5 * U   # the most popular item: most users
+        als.synth_y0(seed=77)
+        Y0 = als.get_y()
+        als.iterate(2)
+        als.sync()
+        X, Y = als.get_x(), als.get_y()
+    Xo, Yo, _, _ = O.als_run(ptr, idx, val, I, Y0, max_iterations=2, convergence_threshold=1e-12,
+                             n_threads=os.cpu_count() or 1)
+    for A, B in ((X, Xo), (Y, Yo)):
+        assert np.linalg.norm(A - B) <= TOL * np.linalg.norm(B)
+        assert np.abs(A - B).max() <= TOL * np.abs(B).max()
