@@ -390,16 +390,16 @@ int launch_gramian_t(als_handle* h, const float* M, long long n_rows) {
   int grid = h->sm_count * 2;
   const long long chunks = (n_rows + kGramChunk - 1) / kGramChunk;
   if (chunks < grid) grid = (int)(chunks > 0 ? chunks : 1);
-  const int n_partials = grid * S::GROUPS;
+  const int n_partials = grid * S::kPartialsPerCta;
   if (n_partials > h->g_partials) {
     dev_free(h, &h->G_partial, (size_t)h->g_partials * h->ks * h->ks);
-    h->g_partials = h->sm_count * 2 * S::GROUPS;
+    h->g_partials = h->sm_count * 2 * S::kPartialsPerCta;
     int rc = dev_alloc(h, &h->G_partial, (size_t)h->g_partials * h->ks * h->ks);
     if (rc != ALS_OK) return rc;
   }
   gramian_partial_kernel<KS><<<grid, kGramThreads, 0, h->stream>>>(M, n_rows, h->G_partial);
   const int kk = KS * KS;
-  gramian_reduce_kernel<<<(kk + 255) / 256, 256, 0, h->stream>>>(h->G_partial, n_partials, kk, h->G);
+  gramian_reduce_kernel<<<(kk + 63) / 64, 64 * kGramReduceSlices, 0, h->stream>>>(h->G_partial, n_partials, KS, h->G);
   h->launches += 2;
   CU(h, cudaGetLastError());
   return ALS_OK;

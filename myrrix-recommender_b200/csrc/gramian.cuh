@@ -15,26 +15,50 @@
 
 namespace als {
 
-constexpr int kGramThreads = 256;
+constexpr int kGramThreads = 288;
 constexpr int kGramChunk = 32;  // rows staged in shared memory per step
 
+// G is symmetric: only the 4x4 tiles on or below the diagonal are accumulated (T (T + 1) / 2 of T^2:
+// 136 of 256 at k = 64 -- the kernel is DFMA-bound, so this is nearly half its time) and the second
+// pass mirrors them.  The tiles are dealt to the threads in GROUPS row-interleaved groups.
 template <int KS>
 struct GramShape {
   static constexpr int T = KS / 4;                 // 4x4 tiles per dimension
-  static constexpr int NT = T * T;                 // tiles in the full matrix
-  static constexpr int TPT = NT >= kGramThreads ? NT / kGramThreads : 1;  // tiles per thread
+  static constexpr int NT = T * (T + 1) / 2;       // tiles on or below the diagonal
+  static constexpr int TPT = NT >= kGramThreads ? (NT + kGramThreads - 1) / kGramThreads : 1;  // tiles per thread
   static constexpr int GROUPS = NT >= kGramThreads ? 1 : kGramThreads / NT;
+  static constexpr int kActive = NT >= kGramThreads ? kGramThreads : GROUPS * NT;
+  static constexpr bool kFold = GROUPS > 2;              // groups folded inside the CTA (k <= 32)
+  static constexpr int kPartialsPerCta = kFold ? 1 : GROUPS;
 };
 
-// partial: [gridDim.x * GROUPS][KS*KS] doubles.
+// lower-triangular tile number -> (ti, tj), ti >= tj
+__device__ __forceinline__ void gram_tile(int tile, int& ti, int& tj) {
+  int i = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+  while ((i + 1) * (i + 2) / 2 <= tile) i++;
+  while (i * (i + 1) / 2 > tile) i--;
+  ti = i;
+  tj = tile - i * (i + 1) / 2;
+}
+
+// partial: [gridDim.x * GROUPS][KS*KS] doubles (entries of the tiles on or below the diagonal).
 template <int KS>
 __global__ void __launch_bounds__(kGramThreads)
 gramian_partial_kernel(const float* __restrict__ M, long long n_rows, double* __restrict__ partial) {
   using S = GramShape<KS>;
   __shared__ double sm[kGramChunk][KS];
   const int tid = threadIdx.x;
+  const bool active = tid < S::kActive;
   const int group = (S::GROUPS > 1) ? tid / S::NT : 0;
   const int tile0 = (S::GROUPS > 1) ? tid % S::NT : tid;
+  int ti[S::TPT], tj[S::TPT];
+#pragma unroll
+  for (int t = 0; t < S::TPT; t++) {
+    const int tile = tile0 + t * kGramThreads;
+    ti[t] = -1;
+    tj[t] = 0;
+    if (active && tile < S::NT) gram_tile(tile, ti[t], tj[t]);
+  }
 
   double acc[S::TPT][16];
 #pragma unroll
@@ -57,45 +81,85 @@ gramian_partial_kernel(const float* __restrict__ M, long long n_rows, double* __
       sm[r][4 * q + 3] = (double)v.w;
     }
     __syncthreads();
+    if (active) {
 #pragma unroll 2
-    for (int r = group; r < kGramChunk; r += S::GROUPS) {
+      for (int r = group; r < kGramChunk; r += S::GROUPS) {
 #pragma unroll
-      for (int t = 0; t < S::TPT; t++) {
-        const int tile = tile0 + t * kGramThreads;
-        const int ti = tile / S::T, tj = tile % S::T;
-        double a[4], b[4];
+        for (int t = 0; t < S::TPT; t++) {
+          if (ti[t] < 0) continue;
+          double a[4], b[4];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          a[e] = sm[r][4 * ti + e];
-          b[e] = sm[r][4 * tj + e];
+          for (int e = 0; e < 4; e++) {
+            a[e] = sm[r][4 * ti[t] + e];
+            b[e] = sm[r][4 * tj[t] + e];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[t][4 * i + j] = fma(a[i], b[j], acc[t][4 * i + j]);
         }
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 4; j++) acc[t][4 * i + j] = fma(a[i], b[j], acc[t][4 * i + j]);
       }
     }
   }
+  if constexpr (S::kFold) {
+    // many small groups (k <= 32): fold them inside the CTA, in group order, so that the second pass
+    // sees one partial per CTA
+    __syncthreads();
+    double* fold = &sm[0][0];  // (KS * KS doubles fit: KS <= 32)
+    for (int e = tid; e < KS * KS; e += kGramThreads) fold[e] = 0.0;
+    for (int g = 0; g < S::GROUPS; g++) {
+      __syncthreads();
+      if (active && group == g) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) fold[(4 * ti[0] + i) * KS + 4 * tj[0] + j] += acc[0][4 * i + j];
+      }
+    }
+    __syncthreads();
+    double* out = partial + (size_t)blockIdx.x * (size_t)(KS * KS);
+    for (int e = tid; e < KS * KS; e += kGramThreads) out[e] = fold[e];
+    return;
+  }
+  if (!active) return;
   double* out = partial + ((size_t)blockIdx.x * S::GROUPS + group) * (size_t)(KS * KS);
 #pragma unroll
   for (int t = 0; t < S::TPT; t++) {
-    const int tile = tile0 + t * kGramThreads;
-    const int ti = tile / S::T, tj = tile % S::T;
+    if (ti[t] < 0) continue;
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) out[(4 * ti + i) * KS + 4 * tj + j] = acc[t][4 * i + j];
+      for (int j = 0; j < 4; j++) out[(4 * ti[t] + i) * KS + 4 * tj[t] + j] = acc[t][4 * i + j];
   }
 }
 
-// G[e] = sum_p partial[p][e] in fixed order (deterministic).
-__global__ void gramian_reduce_kernel(const double* __restrict__ partial, int n_partials, int kk,
-                                      double* __restrict__ G) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= kk) return;
+// G[i][j] = sum_p partial[p][i][j] in a fixed order (deterministic) for the tiles on or below the diagonal;
+// the tiles above it are their mirror images (a[i] * b[j] and b[j] * a[i] are the same product).
+// 64 entries x 4 interleaved slices of the partials per CTA: the loads of a slice are independent, the
+// slices are combined in slice order.
+constexpr int kGramReduceSlices = 4;
+__global__ void __launch_bounds__(64 * kGramReduceSlices)
+gramian_reduce_kernel(const double* __restrict__ partial, int n_partials, int ks, double* __restrict__ G) {
+  __shared__ double part[kGramReduceSlices][64];
+  const int le = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int e = blockIdx.x * 64 + le;
+  const int kk = ks * ks;
+  const int i = e < kk ? e / ks : 0, j = e < kk ? e % ks : 0;
+  const bool mine = e < kk && (i >> 2) >= (j >> 2);  // (the rest is written by the thread of (j, i))
   double s = 0.0;
-  for (int p = 0; p < n_partials; p++) s += partial[(size_t)p * kk + e];
-  G[e] = s;
+  if (mine) {
+#pragma unroll 4
+    for (int p = slice; p < n_partials; p += kGramReduceSlices) s += partial[(size_t)p * kk + e];
+  }
+  part[slice][le] = s;
+  __syncthreads();
+  if (slice == 0 && mine) {
+    double t = part[0][le];
+#pragma unroll
+    for (int q = 1; q < kGramReduceSlices; q++) t += part[q][le];
+    G[e] = t;
+    if ((i >> 2) > (j >> 2)) G[j * ks + i] = t;
+  }
 }
 
 }  // namespace als
