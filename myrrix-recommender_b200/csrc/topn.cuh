@@ -197,12 +197,12 @@ __global__ void __launch_bounds__(kThreads) topn_score_kernel(const __grid_const
     const long long item = tile * kTile + tid;
     const bool valid = item < p.n_items;
     const unsigned char* st = smem + s * S::kStageBytes;
-    // thresholds: the best any CTA has published
-    if (tid < p.n_q) {
-      const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(p.gthr + tid);
-      if (g > thr[tid]) thr[tid] = g;
-    }
-    __syncthreads();
+    // thresholds: this CTA's own or the best any CTA has published, whichever is higher (read per
+    // thread, with the filter words below: no barrier, and the latency hides behind the scoring)
+    unsigned long long gth[kMaxQ];
+#pragma unroll
+    for (int q = 0; q < kMaxQ; q++)
+      gth[q] = q < p.n_q ? *reinterpret_cast<volatile unsigned long long*>(p.gthr + q) : 0ull;
 
     // filter words of my item, one per query, fetched before the scoring so their latency hides
     unsigned exw[kMaxQ];
@@ -218,13 +218,18 @@ __global__ void __launch_bounds__(kThreads) topn_score_kernel(const __grid_const
       for (int j = 0; j < kMaxQ; j++)
         if (j == q) w = exw[j];
       if ((w >> (item & 31)) & 1u) return;
-      const float r = (float)(sum / (double)nvq[q]);  // RecommendIterator.java:98
+      const int nv = nvq[q];
+      const float r = (float)(nv == 1 ? sum : sum / (double)nv);  // RecommendIterator.java:98 (x / 1.0 == x)
       if (!isfinite(r)) {
         *p.nonfinite = 1;
         return;
       }
       const unsigned long long key = make_key(r, (unsigned)item);
-      if (key > thr[q]) {
+      unsigned long long th = thr[q];
+#pragma unroll
+      for (int j = 0; j < kMaxQ; j++)
+        if (j == q && gth[j] > th) th = gth[j];
+      if (key > th) {
         const int pos = atomicAdd(&cnt[q], 1);
         buf[q * kCap + pos] = key;  // pos < kCap: at most kTile insertions since the last prune check
       }

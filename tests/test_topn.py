@@ -169,3 +169,22 @@ def test_recommender_mirror_with_long_ids(M):
         assert got == [(int(iid[i]), float(v)) for i, v in zip(oi, ov)]
         with pytest.raises(NoSuchUserException):
             rec.recommend(123, 5)
+
+
+@pytest.mark.gpu
+def test_denormal_products_and_huge_scores_keep_the_reference_arithmetic(M):
+    """Products below 1.2e-38 (denormal floats) and sums near the float range: the widening of the
+    fp32 products to fp64 must stay exact (the kernel leaves its integer fast path for these)."""
+    k, I = 8, 700
+    rng = np.random.default_rng(9)
+    with M.NativeALS(k, device=0) as als:
+        als.set_interactions(1, I, np.array([0, 1], np.int64), np.array([0], np.int32), np.array([1], np.float32))
+        for scale_y, scale_x in ((1e-20, 1e-19), (1e-30, 1e-9), (1e18, 1e19), (1.0, 1.0)):
+            Y = (rng.standard_normal((I, k)) * scale_y).astype(np.float32)
+            Y[::7] = 0.0
+            f = (rng.standard_normal((2, k)) * scale_x).astype(np.float32)
+            als.set_y(Y)
+            ids, vals = als.top_n("y", f, 50)
+            oi, ov = T.top_n_sorted(T.scores(Y, f), 50)
+            assert np.array_equal(ids, oi), (scale_y, scale_x)
+            assert np.array_equal(vals, ov)
