@@ -152,10 +152,16 @@ struct Mix {
   // phase early and pass on the stale parity -- measured: deadlock with 8 slots and 10 warps).
   static constexpr int kBSlots = NCHOL;
   static constexpr bool kSetReg = SETREG;
-  static constexpr int kRegsProd = (kThreads == 640 && NCHOL == 8) ? 80 : 96;
+  // register budget per role (setmaxnreg): 640 threads launch at 96 registers -- drain 64, Cholesky 128,
+  // producers 80 (8 + 7 mix) or 96; 768 threads (4 + 15 mix) launch at 80 -- drain 64, Cholesky 96, producers 80
+  static constexpr int kLaunchRegs = kThreads == 640 ? 96 : 80;
+  static constexpr int kRegsProd = (kThreads == 640 && NCHOL != 8) ? 96 : 80;
+  static constexpr int kRegsCholMix = kThreads == 640 ? kRegsChol : 96;
   static_assert(kThreads <= 1024, "threads per CTA");
-  static_assert(!SETREG || (NCHOL % 4 == 0 && (NPROD + 1) % 4 == 0 && kThreads == 640), "setmaxnreg: warpgroups per role");
-  static_assert(!SETREG || 32 * (kRegsDrain + (NCHOL / 4) * kRegsChol + ((16 - NCHOL) / 4) * kRegsProd) <= 5 * 96 * 32,
+  static_assert(!SETREG || (NCHOL % 4 == 0 && (NPROD + 1) % 4 == 0 && (kThreads == 640 || kThreads == 768)),
+                "setmaxnreg: warpgroups per role");
+  static_assert(!SETREG || 128 * (kRegsDrain + (NCHOL / 4) * kRegsCholMix + ((NPROD + 1) / 4) * kRegsProd) <=
+                               kThreads * kLaunchRegs,
                 "register pool");
   static_assert(!kAsync || kStages >= (kAhead + 1) * kProdWarps, "ring too shallow for the gather depth");
 };
@@ -440,7 +446,7 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
   const long long row_step = gridDim.x;
 
   if (warp >= kFirstProd) {
-   if constexpr (MX::kSetReg && kRegsProd < 96) umma::reg_dealloc<kRegsProd>();
+   if constexpr (MX::kSetReg && kRegsProd < MX::kLaunchRegs) umma::reg_dealloc<kRegsProd>();
    if (warp < kMmaWarp) {
     if constexpr (MX::kAsync) {
     // =========================== producers: async gather + in-place conversion ========
@@ -904,7 +910,7 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
     }
   } else {
     // =========================== Cholesky warps ======================================
-    if constexpr (MX::kSetReg && kRegsChol > 96) umma::reg_alloc<kRegsChol>();
+    if constexpr (MX::kSetReg && MX::kRegsCholMix > MX::kLaunchRegs) umma::reg_alloc<MX::kRegsCholMix>();
     const int cw = warp - kFirstChol;
     constexpr int kGroups = (ALS_V2_LOCKSTEP > kCholWarps / 2) ? kCholWarps / 2 : ALS_V2_LOCKSTEP;
     constexpr int kGroupWarps = kGroups ? kCholWarps / kGroups : 1;
