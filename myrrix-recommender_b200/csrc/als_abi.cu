@@ -147,6 +147,7 @@ struct als_handle {
   // peer replicas of X and Y (cudaIpc mappings; entry `rank` is unused): finished rows are pushed
   // into them from the solve epilogue.  p2p = false -> exchange by ncclAllGather after the kernel.
   bool p2p = false, p2p_disabled = false;
+  bool factors_ipc = false;  // X / Y are plain cudaMalloc allocations (mappable by peers), not pool memory
   float* peer_X[16] = {nullptr};
   float* peer_Y[16] = {nullptr};
   // profiling
@@ -313,12 +314,28 @@ int setup_peers(als_handle* h) {
   return ALS_OK;
 }
 
+void free_factors(als_handle* h) {
+  if (h->factors_ipc) {
+    dev_free_ipc(h, &h->X, (size_t)h->users_alloc * h->ks);
+    dev_free_ipc(h, &h->Y, (size_t)h->items_alloc * h->ks);
+  } else {
+    dev_free(h, &h->X, (size_t)h->users_alloc * h->ks);
+    dev_free(h, &h->Y, (size_t)h->items_alloc * h->ks);
+  }
+  // cached views of the old allocations
+  h->gather_map_base[0] = h->gather_map_base[1] = nullptr;
+}
+
 int alloc_factors(als_handle* h) {
   // Factor replicas are padded to world * block rows so the per-half all-gather is a
   // plain in-place ncclAllGather of equal blocks.
   const long long ua = block_rows(h->n_users, h->world) * h->world;
   const long long ia = block_rows(h->n_items, h->world) * h->world;
-  if (h->X && ua == h->users_alloc && h->Y && ia == h->items_alloc) return ALS_OK;
+  // single-GPU handles take the replicas from the pool like everything else (cudaFree / cudaMalloc of
+  // 2.8 GB cost 25-400 ms per model build depending on the box); only handles with a communicator
+  // need cudaIpc-mappable (plain) allocations
+  const bool want_ipc = h->comm != nullptr;
+  if (h->X && ua == h->users_alloc && h->Y && ia == h->items_alloc && h->factors_ipc == want_ipc) return ALS_OK;
   if (h->p2p) {
     // collective: every rank re-allocates for the same new sizes; nobody frees a replica while
     // a peer still has it mapped
@@ -326,13 +343,18 @@ int alloc_factors(als_handle* h) {
     g_nccl.AllReduce(h->d_flag + 3, h->d_flag + 3, 1, ncclInt, ncclMin, h->comm, h->stream);
     CU(h, cudaStreamSynchronize(h->stream));
   }
-  dev_free_ipc(h, &h->X, (size_t)h->users_alloc * h->ks);
-  dev_free_ipc(h, &h->Y, (size_t)h->items_alloc * h->ks);
+  free_factors(h);
   h->users_alloc = ua;
   h->items_alloc = ia;
+  h->factors_ipc = want_ipc;
   int rc;
-  if ((rc = dev_alloc_ipc(h, &h->X, (size_t)ua * h->ks)) != ALS_OK) return rc;
-  if ((rc = dev_alloc_ipc(h, &h->Y, (size_t)ia * h->ks)) != ALS_OK) return rc;
+  if (want_ipc) {
+    if ((rc = dev_alloc_ipc(h, &h->X, (size_t)ua * h->ks)) != ALS_OK) return rc;
+    if ((rc = dev_alloc_ipc(h, &h->Y, (size_t)ia * h->ks)) != ALS_OK) return rc;
+  } else {
+    if ((rc = dev_alloc(h, &h->X, (size_t)ua * h->ks)) != ALS_OK) return rc;
+    if ((rc = dev_alloc(h, &h->Y, (size_t)ia * h->ks)) != ALS_OK) return rc;
+  }
   CU(h, cudaMemsetAsync(h->X, 0, sizeof(float) * (size_t)ua * h->ks, h->stream));
   CU(h, cudaMemsetAsync(h->Y, 0, sizeof(float) * (size_t)ia * h->ks, h->stream));
   return setup_peers(h);
@@ -715,7 +737,7 @@ int build_transpose_from(als_handle* h, const Csr& A, long long col_begin, long 
   auto cleanup = [&]() {
     dev_free(h, &keys_in, n); dev_free(h, &keys_out, n);
     dev_free(h, &pk_in, n); dev_free(h, &pk_out, n);
-    if (tmp) { cudaFree(tmp); h->device_bytes -= (long long)tmp_bytes; }
+    if (tmp) { cudaFreeAsync(tmp, h->stream); h->device_bytes -= (long long)tmp_bytes; }
   };
   if ((rc = dev_alloc(h, &keys_in, n)) != ALS_OK || (rc = dev_alloc(h, &keys_out, n)) != ALS_OK ||
       (rc = dev_alloc(h, &pk_in, n)) != ALS_OK || (rc = dev_alloc(h, &pk_out, n)) != ALS_OK) {
@@ -729,7 +751,7 @@ int build_transpose_from(als_handle* h, const Csr& A, long long col_begin, long 
   while ((1LL << end_bit) < n_cols && end_bit < 31) end_bit++;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, pk_in,
                                                   pk_out, (int)n, 0, end_bit, h->stream);
-  if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+  if (e == cudaSuccess) e = cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, h->stream);
   if (e == cudaSuccess) {
     h->device_bytes += (long long)tmp_bytes;
     e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, pk_in, pk_out, (int)n, 0,
@@ -1116,7 +1138,7 @@ int als_destroy(als_handle* h) {
   for (int w = 0; w < 2; w++) dev_free(h, &h->d_order[w], (size_t)h->order_rows[w]);
   free_csr(h, &h->by_user);
   free_csr(h, &h->by_item);
-  cudaFree(h->X); cudaFree(h->Y);  // (cudaIpc-mappable: plain allocations)
+  free_factors(h);
   // pool allocations go back to the pool (stream-ordered; nothing is unmapped)
   void* pooled[] = {h->G, h->G_partial, h->d_status, h->d_ticket, h->d_rank, h->d_scratch, h->d_retry_rows,
                     h->d_retry_count, h->d_retry_total, h->d_flag, h->d_probe_idx, h->d_probe_out,
