@@ -102,6 +102,25 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst_saddr, const CUtensorMa
       : "memory");
 }
 
+#ifndef ALS_V2_PACE_CHOL_NS
+#define ALS_V2_PACE_CHOL_NS 0
+#endif
+#ifndef ALS_V2_PACE_DRAIN_NS
+#define ALS_V2_PACE_DRAIN_NS 0
+#endif
+#ifndef ALS_V2_PACE_MMA_NS
+#define ALS_V2_PACE_MMA_NS 0
+#endif
+#ifndef ALS_V2_PACE_CHOL_SHORT_NS
+#define ALS_V2_PACE_CHOL_SHORT_NS 0
+#endif
+#ifndef ALS_V2_PACE_DRAIN_SHORT_NS
+#define ALS_V2_PACE_DRAIN_SHORT_NS 0
+#endif
+#ifndef ALS_V2_PACE_MMA_SHORT_NS
+#define ALS_V2_PACE_MMA_SHORT_NS 0
+#endif
+
 // extra own-stages of look-ahead for a producer's index / value loads (see the producer loop)
 #ifndef ALS_V2_FETCH_EXTRA
 #define ALS_V2_FETCH_EXTRA 0
@@ -152,6 +171,11 @@ struct Mix {
   // phase early and pass on the stale parity -- measured: deadlock with 8 slots and 10 warps).
   static constexpr int kBSlots = NCHOL;
   static constexpr bool kSetReg = SETREG;
+  // poll pacing (ns between polls) of the consumer roles, which wait most of the time when the
+  // producers bound the kernel (long rows); 0: plain wait
+  static constexpr int kPaceChol = NCHOL == 4 ? ALS_V2_PACE_CHOL_NS : ALS_V2_PACE_CHOL_SHORT_NS;
+  static constexpr int kPaceDrain = NCHOL == 4 ? ALS_V2_PACE_DRAIN_NS : ALS_V2_PACE_DRAIN_SHORT_NS;
+  static constexpr int kPaceMma = NCHOL == 4 ? ALS_V2_PACE_MMA_NS : ALS_V2_PACE_MMA_SHORT_NS;
   // register budget per role (setmaxnreg): 640 threads launch at 96 registers -- drain 64, Cholesky 128,
   // producers 80 (8 + 7 mix) or 96; 768 threads (4 + 15 mix) launch at 80 -- drain 64, Cholesky 96, producers 80
   static constexpr int kLaunchRegs = kThreads == 640 ? 96 : 80;
@@ -792,7 +816,7 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
             if (lane == 0) atomicAdd(&umma::g_wait_cycles[3], (unsigned long long)(clock64() - t0));
           }
 #else
-          mbar_wait_addr(full_a, par);
+          umma::mbar_wait_addr_paced<MX::kPaceMma>(full_a, par);
 #endif
           tc_fence_after_sync();
 #pragma unroll
@@ -854,7 +878,11 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
         mbar_wait_id(&w_empty[ws], (uint32_t)(((useq / kWSlots) & 1) ^ 1), 4);
         for (int seg = 0; seg < nseg; seg++, gseg++) {
           const int a = (int)(gseg % kAccSlots);
+#if defined(ALS_PROFILE_WAITS) || defined(ALS_WATCHDOG)
           mbar_wait_id(&acc_full[a], (gseg / kAccSlots) & 1, 5);
+#else
+          umma::mbar_wait_paced<MX::kPaceDrain>(&acc_full[a], (gseg / kAccSlots) & 1);
+#endif
           tc_fence_after_sync();
           const uint32_t tcol = tmem_base + (uint32_t)(a * G::kN);
           const float* src = (seg == 0) ? ng : slot;  // later segments add to what this thread stored
@@ -933,7 +961,11 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
         const int nst = (cnt + E - 1) / E;
         const int smod = __shfl_sync(kFull, smod_l, ib);
         const int bs = useq % kBSlots;
+#if defined(ALS_PROFILE_WAITS) || defined(ALS_WATCHDOG)
         mbar_wait_id(&b_full[bs], (uint32_t)((useq / kBSlots) & 1), 7);
+#else
+        umma::mbar_wait_paced<MX::kPaceChol>(&b_full[bs], (uint32_t)((useq / kBSlots) & 1));
+#endif
         float b[CB::kS];
 #pragma unroll
         for (int s = 0; s < CB::kS; s++) b[s] = 0.f;
@@ -951,7 +983,11 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
         if (lane == 0) mbar_arrive(&b_empty[bs]);
         const int ws = useq % kWSlots;
         float* slot = slots + ws * WP::kFloats;
+#if defined(ALS_PROFILE_WAITS) || defined(ALS_WATCHDOG)
         mbar_wait_id(&w_full[ws], (uint32_t)((useq / kWSlots) & 1), 6);
+#else
+        umma::mbar_wait_paced<MX::kPaceChol>(&w_full[ws], (uint32_t)((useq / kWSlots) & 1));
+#endif
 #ifdef ALS_PROFILE_WAITS
         const long long tb = clock64();
         if (kGroups) bar_sync(1 + cw / kGroupWarps, kGroupWarps * 32);

@@ -247,6 +247,47 @@ __device__ __forceinline__ void mma_commit_addr_elect(uint32_t bar_addr) {
       "}\n" ::"r"(bar_addr)
       : "memory");
 }
+// Wait with a bounded poll rate: NS > 0 sleeps about NS nanoseconds between polls.  Every poll of an
+// mbarrier is a shared-memory access: with the plain wait the nine consumer warps of the long-row
+// mix, which wait most of the time, polled away a quarter of the SM's shared-memory bandwidth -- the
+// resource that bounds that kernel.
+template <int NS>
+__device__ __forceinline__ void mbar_wait_paced(uint64_t* bar, uint32_t parity) {
+  if constexpr (NS > 0) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(NS);
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+template <int NS>
+__device__ __forceinline__ void mbar_wait_addr_paced(uint32_t bar_addr, uint32_t parity) {
+  if constexpr (NS > 0) {
+    for (;;) {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t"
+          "}\n"
+          : "=r"(ok)
+          : "r"(bar_addr), "r"(parity)
+          : "memory");
+      if (ok) break;
+      __nanosleep(NS);
+    }
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@!p bra WAIT_%=;\n\t"
+        "}\n" ::"r"(bar_addr), "r"(parity), "r"(1000000u)
+        : "memory");
+  }
+}
+
 // spin on an mbarrier given by its shared-window address
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
   asm volatile(
