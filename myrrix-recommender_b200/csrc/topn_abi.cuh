@@ -14,6 +14,7 @@ struct TopNState {
   int* ints = nullptr;        // qrow | vec_query of a pass, or the users of a batch
   size_t ints_cap = 0;
   float* vecs = nullptr;      // [kMaxVec][ks] staging of caller-supplied feature vectors
+  int* pack = nullptr;        // single-query results in one read-back: items[kMaxN] | values[kMaxN] | count | nonfinite
   int* out_items = nullptr;
   float* out_values = nullptr;
   int* out_counts = nullptr;
@@ -52,7 +53,7 @@ void topn_free(als_handle* h) {
   TopNState* t = h->topn;
   if (!t) return;
   cudaFree(t->excl); cudaFree(t->tmp); cudaFree(t->cand); cudaFree(t->gthr); cudaFree(t->nonfinite);
-  cudaFree(t->ints); cudaFree(t->vecs); cudaFree(t->out_items); cudaFree(t->out_values); cudaFree(t->out_counts);
+  cudaFree(t->ints); cudaFree(t->vecs); cudaFree(t->pack); cudaFree(t->out_items); cudaFree(t->out_values); cudaFree(t->out_counts);
   delete t;
   h->topn = nullptr;
 }
@@ -150,6 +151,7 @@ int topn_prepare(als_handle* h, const float* F, long long rows, int how_many, si
     CU(h, cudaMalloc(&t->gthr, sizeof(unsigned long long) * topn::kMaxQ));
     CU(h, cudaMalloc(&t->nonfinite, sizeof(int)));
     CU(h, cudaMalloc(&t->vecs, sizeof(float) * (size_t)topn::kMaxVec * kMaxFeatures));
+    CU(h, cudaMalloc(&t->pack, sizeof(int) * (2 * topn::kMaxN + 2)));
   }
   t->grid = h->sm_count * 2;
   int rc;
@@ -248,7 +250,16 @@ static int topn_one_query(als_handle* h, int32_t which, const float* features, c
     if (!rows_of_x || which != 1) return fail(h, ALS_E_ARG, "known items are defined for user queries against items");
     const Csr& R = h->by_user;
     bool first = true;
-    for (int v = 0; v < n_vec; v++) {
+    if (n_vec == 1) {
+      // one user: mark its row (a row without entries marks nothing) -- no need to know its length here
+      const long long row = (long long)rows_of_x[0] - R.row_begin;
+      if (row < 0 || row >= R.rows)
+        return fail(h, ALS_E_ARG, "user %d is not in this rank's block: its known items live on another rank", rows_of_x[0]);
+      topn::mark_row_kernel<<<8, 256, 0, h->stream>>>(R.ptr, R.idx, row, t->excl);
+      h->launches += 1;
+      filtered = true;
+    }
+    for (int v = 0; v < n_vec && n_vec > 1; v++) {
       const long long row = (long long)rows_of_x[v] - R.row_begin;
       if (row < 0 || row >= R.rows)
         return fail(h, ALS_E_ARG, "user %d is not in this rank's block: its known items live on another rank", rows_of_x[v]);
@@ -277,7 +288,7 @@ static int topn_one_query(als_handle* h, int32_t which, const float* features, c
     filtered = true;
   }
   CU(h, cudaMemsetAsync(t->gthr, 0, sizeof(unsigned long long) * topn::kMaxQ, h->stream));
-  CU(h, cudaMemsetAsync(t->nonfinite, 0, sizeof(int), h->stream));
+  CU(h, cudaMemsetAsync(t->pack + 2 * topn::kMaxN, 0, 2 * sizeof(int), h->stream));
   topn::Params p;
   p.qbase = qbase;
   p.qrow = t->ints;
@@ -290,15 +301,29 @@ static int topn_one_query(als_handle* h, int32_t which, const float* features, c
   p.how_many = how_many;
   p.gthr = t->gthr;
   p.cand = t->cand;
-  p.nonfinite = t->nonfinite;
+  p.nonfinite = t->pack + 2 * topn::kMaxN + 1;
+  // the pass's results land in the packed buffer: one read-back, one synchronisation
+  int* const oi = t->out_items;
+  float* const ov = t->out_values;
+  int* const oc = t->out_counts;
+  t->out_items = t->pack;
+  t->out_values = reinterpret_cast<float*>(t->pack + topn::kMaxN);
+  t->out_counts = t->pack + 2 * topn::kMaxN;
   nvtxRangePushA("als:top_n");
   rc = topn_launch(h, t, p);
   nvtxRangePop();
+  t->out_items = oi;
+  t->out_values = ov;
+  t->out_counts = oc;
   if (rc != ALS_OK) return rc;
-  CU(h, cudaMemcpyAsync(out_ids, t->out_items, sizeof(int) * (size_t)how_many, cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaMemcpyAsync(out_values, t->out_values, sizeof(float) * (size_t)how_many, cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaMemcpyAsync(out_count, t->out_counts, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  return topn_check_nonfinite(h, t);
+  int host[2 * topn::kMaxN + 2];
+  CU(h, cudaMemcpyAsync(host, t->pack, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (host[2 * topn::kMaxN + 1]) return fail(h, ALS_E_NONFINITE, "Bad recommendation value (RecommendIterator.java:99)");
+  memcpy(out_ids, host, sizeof(int) * (size_t)how_many);
+  memcpy(out_values, host + topn::kMaxN, sizeof(float) * (size_t)how_many);
+  *out_count = host[2 * topn::kMaxN];
+  return ALS_OK;
 }
 
 int als_top_n(als_handle* h, int32_t which, const float* features, int32_t n_vectors, const int32_t* exclude,

@@ -42,7 +42,7 @@ with M.NativeALS(k, device=0) as als:
     t1 = (time.perf_counter() - t0) / reps
     bytes_pass = I * 4 * als.info().padded_features
     out["single_query"] = {"seconds": t1, "gbs": bytes_pass / t1 / 1e9, "frac_of_hbm": bytes_pass / t1 / 1e9 / peak,
-                           "note": "host call to host result (known-item lookup, 5 launches, read-back)"}
+                           "note": "host call to host result (filter bitmap, score + merge kernels, one packed read-back)"}
     als.recommend_batch(users[:64], N)
     t0 = time.perf_counter()
     items, values, counts = als.recommend_batch(users, N)
