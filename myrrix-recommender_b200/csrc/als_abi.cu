@@ -633,6 +633,10 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
     const int mi = which == 0 ? 1 : 0;  // the X half gathers rows of Y and vice versa
     if ((h->ks == 64 || h->ks == 32) && !h->legacy_umma) {
       const long long m_rows = which == 0 ? h->n_items : h->n_users;
+      if (m_rows >= (long long)v2::kOobRow) {  // (the gathers' "no entry" row index must lie past the tensor)
+        nvtxRangePop();
+        return fail(h, ALS_E_UNSUPPORTED, "factor matrices of 2^30 rows or more");
+      }
       if (h->gather_map_base[mi] != M || h->gather_map_rows[mi] != m_rows) {
         EncodeTiledFn enc = encode_tiled_fn();
         if (!enc) { nvtxRangePop(); return fail(h, ALS_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver"); }
