@@ -97,6 +97,21 @@ struct als_handle {
   int* d_order[2] = {nullptr, nullptr};
   long long order_rows[2] = {0, 0};
   bool order_valid[2] = {false, false};
+  // long rows split into chunks for the tensor-core kernel (ensure_split): virtual rows per orientation
+  struct Split {
+    bool valid = false;      // built for the current interaction arrays
+    long long rows = 0;      // rows of the orientation it was built for
+    long long n_virtual = 0; // virtual rows (= rows when nothing is split)
+    long long n_acc = 0;     // split rows (0: the orientation is walked as stored)
+    long long* vptr = nullptr;
+    int* vrow = nullptr;
+    int* vacc = nullptr;
+    int* acc_chunks = nullptr;
+    float* gacc = nullptr;
+    int* gcount = nullptr;
+    size_t acc_floats = 0;   // floats of one accumulation record
+  } split[2];
+  long long split_limit = 8192;  // entries; MYRRIX_ALS_SPLIT_ROWS (0: never split)
   // fold-in solver state of the generation (als_set_fold_in_state): [0] X'X, [1] Y'Y
   double* fi_qrt[2] = {nullptr, nullptr};
   double* fi_rdiag[2] = {nullptr, nullptr};
@@ -242,8 +257,20 @@ void dev_free_ipc(als_handle* h, T** p, size_t count) {
   }
 }
 
+void free_split(als_handle* h, int which) {
+  als_handle::Split& s = h->split[which];
+  dev_free(h, &s.vptr, (size_t)s.n_virtual + 1);
+  dev_free(h, &s.vrow, (size_t)s.n_virtual);
+  dev_free(h, &s.vacc, (size_t)s.n_virtual);
+  dev_free(h, &s.acc_chunks, (size_t)s.n_acc);
+  dev_free(h, &s.gacc, (size_t)s.n_acc * s.acc_floats);
+  dev_free(h, &s.gcount, (size_t)s.n_acc);
+  s = als_handle::Split();
+}
+
 void free_csr(als_handle* h, Csr* c) {
   h->order_valid[0] = h->order_valid[1] = false;
+  h->split[0].valid = h->split[1].valid = false;
   dev_free(h, &c->ptr, (size_t)c->rows + 1);
   dev_free(h, &c->idx, (size_t)c->nnz);
   dev_free(h, &c->val, (size_t)c->nnz);
@@ -575,6 +602,67 @@ int ensure_row_order(als_handle* h, const Csr& R, int which) {
   return ALS_OK;
 }
 
+// Rows longer than h->split_limit entries are walked as several virtual rows (equal chunks) by the
+// tensor-core kernel, so that one 10^5..10^6-entry row of power-law data (a popular item's column) is shared by
+// many CTAs instead of deciding the kernel's tail; see RowUpdateParams::vrow.  Built once per
+// interaction array.  n_acc == 0 afterwards: nothing to split, the orientation is walked as stored.
+int ensure_split(als_handle* h, const Csr& R, int which) {
+  als_handle::Split& s = h->split[which];
+  if (s.valid && s.rows == R.rows) return ALS_OK;
+  free_split(h, which);
+  s.rows = R.rows;
+  s.n_virtual = R.rows;
+  if (h->split_limit <= 0 || R.rows == 0 || R.nnz <= h->split_limit) { s.valid = true; return ALS_OK; }
+  const size_t n1 = (size_t)R.rows + 1;
+  long long *nch = nullptr, *vfirst = nullptr;
+  int *is_long = nullptr, *accfirst = nullptr;
+  void* tmp = nullptr;
+  int rc = ALS_OK;
+  auto done = [&](int code) {
+    if (tmp) cudaFreeAsync(tmp, h->stream);
+    dev_free(h, &nch, n1); dev_free(h, &vfirst, n1); dev_free(h, &is_long, n1); dev_free(h, &accfirst, n1);
+    return code;
+  };
+  if ((rc = dev_alloc(h, &nch, n1)) != ALS_OK || (rc = dev_alloc(h, &vfirst, n1)) != ALS_OK ||
+      (rc = dev_alloc(h, &is_long, n1)) != ALS_OK || (rc = dev_alloc(h, &accfirst, n1)) != ALS_OK)
+    return done(rc);
+  split_counts_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(R.ptr, R.rows, h->split_limit, nch, is_long);
+  size_t b1 = 0, b2 = 0;
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, b1, nch, vfirst, (int)n1, h->stream);
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, b2, is_long, accfirst, (int)n1, h->stream);
+  const size_t tb = b1 > b2 ? b1 : b2;
+  if (e == cudaSuccess) e = cudaMallocAsync(&tmp, tb ? tb : 1, h->stream);
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, b1, nch, vfirst, (int)n1, h->stream);
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, b2, is_long, accfirst, (int)n1, h->stream);
+  long long n_virtual = 0;
+  int n_acc = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&n_virtual, vfirst + R.rows, sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&n_acc, accfirst + R.rows, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  h->launches += 3;
+  if (e != cudaSuccess) return done(fail(h, ALS_E_CUDA, "row split: %s", cudaGetErrorString(e)));
+  if (n_acc == 0) { s.valid = true; return done(ALS_OK); }
+  if (n_virtual >= (1LL << 31)) return done(fail(h, ALS_E_UNSUPPORTED, "more than 2^31 - 1 local (virtual) rows"));
+  s.n_virtual = n_virtual;
+  s.n_acc = n_acc;
+  s.acc_floats = (h->ks == 64 ? (size_t)WPanels<64>::kFloats : (size_t)WPanels<32>::kFloats) + (size_t)h->ks;
+  if ((rc = dev_alloc(h, &s.vptr, (size_t)n_virtual + 1)) != ALS_OK || (rc = dev_alloc(h, &s.vrow, (size_t)n_virtual)) != ALS_OK ||
+      (rc = dev_alloc(h, &s.vacc, (size_t)n_virtual)) != ALS_OK || (rc = dev_alloc(h, &s.acc_chunks, (size_t)n_acc)) != ALS_OK ||
+      (rc = dev_alloc(h, &s.gacc, (size_t)n_acc * s.acc_floats)) != ALS_OK || (rc = dev_alloc(h, &s.gcount, (size_t)n_acc)) != ALS_OK) {
+    free_split(h, which);
+    return done(rc);
+  }
+  split_fill_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(R.ptr, R.rows, h->split_limit, vfirst, accfirst, s.vptr, s.vrow,
+                                                           s.vacc, s.acc_chunks);
+  h->launches += 1;
+  if ((e = cudaGetLastError()) != cudaSuccess) {
+    free_split(h, which);
+    return done(fail(h, ALS_E_CUDA, "row split: %s", cudaGetErrorString(e)));
+  }
+  s.valid = true;
+  return done(ALS_OK);
+}
+
 int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, int which) {
   RowUpdateParams p;
   p.row_ptr = R.ptr;
@@ -597,8 +685,27 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
   p.row_list = nullptr;
   p.row_list_count = nullptr;
   p.row_order = nullptr;
+  p.vrow = nullptr;
+  p.vacc = nullptr;
+  p.acc_chunks = nullptr;
+  p.real_ptr = R.ptr;
+  p.gacc = nullptr;
+  p.gcount = nullptr;
+  // the second-generation tensor-core kernel walks rows of more than split_limit entries as chunks
+  const bool v2_kernel = h->kernel == ALS_KERNEL_TCGEN05 && (h->ks == 64 || h->ks == 32) && !h->legacy_umma;
+  const als_handle::Split* sp = nullptr;
+  if (v2_kernel) {
+    const int src = ensure_split(h, R, which);
+    if (src != ALS_OK) return src;
+    if (h->split[which].n_acc > 0) sp = &h->split[which];
+  }
+  Csr Rv = R;  // the rows the kernel walks (virtual rows when split)
+  if (sp) {
+    Rv.ptr = sp->vptr;
+    Rv.rows = sp->n_virtual;
+  }
   if (!h->no_row_order && R.rows > 0) {
-    const int orc = ensure_row_order(h, R, which);
+    const int orc = ensure_row_order(h, Rv, which);
     if (orc != ALS_OK) return orc;
     p.row_order = h->d_order[which];
   }
@@ -653,6 +760,18 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
       }
     }
     const CUtensorMap& tm = h->gather_map[mi];
+    const RowUpdateParams p_rows = p;  // the rows as stored: what the fp64 re-solve below walks
+    if (sp) {
+      p.row_ptr = sp->vptr;
+      p.n_rows = sp->n_virtual;
+      p.vrow = sp->vrow;
+      p.vacc = sp->vacc;
+      p.acc_chunks = sp->acc_chunks;
+      p.gacc = sp->gacc;
+      p.gcount = sp->gcount;
+      cudaMemsetAsync(sp->gacc, 0, (size_t)sp->n_acc * sp->acc_floats * sizeof(float), h->stream);
+      cudaMemsetAsync(sp->gcount, 0, (size_t)sp->n_acc * sizeof(int), h->stream);
+    }
     if (h->ks == 64 && !h->legacy_umma) {
       rc = long_rows ? launch_row_update_v2_t<64, v2::MixLong>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err))
                      : launch_row_update_v2_t<64, v2::MixShort>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err));
@@ -668,6 +787,7 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
       // CUDA-core kernel in row-list mode; it exits immediately when the list is empty.
       accumulate_count_kernel<<<1, 1, 0, h->stream>>>(h->d_retry_count, h->d_retry_total);
       h->launches += 1;
+      p = p_rows;
       RowUpdateParams q = p;
       q.row_list = h->d_retry_rows;
       q.row_list_count = h->d_retry_count;
@@ -1090,6 +1210,10 @@ int als_create(const als_config* cfg, als_handle** out) {
   if (const char* e = getenv("MYRRIX_ALS_V1")) h->legacy_umma = atoi(e) != 0;
   if (const char* e = getenv("MYRRIX_ALS_NO_P2P")) h->p2p_disabled = atoi(e) != 0;
   if (const char* e = getenv("MYRRIX_ALS_NO_ROW_ORDER")) h->no_row_order = atoi(e) != 0;
+  if (const char* e = getenv("MYRRIX_ALS_SPLIT_ROWS")) {
+    const long long v = atoll(e);
+    h->split_limit = v <= 0 ? 0 : (v < 64 ? 64 : v);
+  }
   CU(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   {
@@ -1140,6 +1264,7 @@ int als_destroy(als_handle* h) {
   topn_free(h);
   for (int w = 0; w < 2; w++) { cudaFree(h->fi_qrt[w]); cudaFree(h->fi_rdiag[w]); cudaFree(h->fi_perm[w]); }
   for (int w = 0; w < 2; w++) dev_free(h, &h->d_order[w], (size_t)h->order_rows[w]);
+  for (int w = 0; w < 2; w++) free_split(h, w);
   free_csr(h, &h->by_user);
   free_csr(h, &h->by_item);
   free_factors(h);

@@ -101,6 +101,54 @@ __global__ void stop_rule_kernel(const double* __restrict__ fresh, double* __res
   out[1] = total_weight;
 }
 
+// ---- long rows split into chunks (virtual rows; see RowUpdateParams) -------------------------------
+// nch[r] = chunks of row r (1 unless it has more than `limit` entries), is_long[r] = 1 for split rows
+__global__ void split_counts_kernel(const long long* __restrict__ ptr, long long n_rows, long long limit,
+                                    long long* __restrict__ nch, int* __restrict__ is_long) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r <= n_rows; r += stride) {
+    long long c = 0;
+    int l = 0;
+    if (r < n_rows) {
+      const long long n = ptr[r + 1] - ptr[r];
+      c = n > limit ? (n + limit - 1) / limit : 1;
+      l = c > 1;
+    }
+    nch[r] = c;
+    is_long[r] = l;
+  }
+}
+// vfirst / accfirst: exclusive prefix sums of nch / is_long.  Chunks of a row are equal (rounded up to a
+// multiple of 32 entries so that all but the last end on a stage boundary).
+__global__ void split_fill_kernel(const long long* __restrict__ ptr, long long n_rows, long long limit,
+                                  const long long* __restrict__ vfirst, const int* __restrict__ accfirst,
+                                  long long* __restrict__ vptr, int* __restrict__ vrow, int* __restrict__ vacc,
+                                  int* __restrict__ acc_chunks) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+    const long long e0 = ptr[r], n = ptr[r + 1] - e0;
+    const long long c = n > limit ? (n + limit - 1) / limit : 1;
+    const long long v0 = vfirst[r];
+    if (c == 1) {
+      vptr[v0] = e0;
+      vrow[v0] = (int)r;
+      vacc[v0] = -1;
+    } else {
+      const long long len = ((n + c - 1) / c + 31) / 32 * 32;
+      const int a = accfirst[r];
+      long long used = 0;
+      for (long long j = 0; j < c; j++) {  // (a trailing chunk can come out empty: it is skipped like an empty row)
+        vptr[v0 + j] = e0 + (j * len < n ? j * len : n);
+        vrow[v0 + j] = (int)r;
+        vacc[v0 + j] = a;
+        if (j * len < n) used++;
+      }
+      acc_chunks[a] = (int)used;
+    }
+    if (r == n_rows - 1) vptr[vfirst[n_rows]] = ptr[n_rows];
+  }
+}
+
 // keys[r] = entries of row r, vals[r] = r: sorted by key, descending, they give the visiting order of
 // the row updates (longest rows first)
 __global__ void row_length_keys_kernel(const long long* __restrict__ ptr, long long n_rows, unsigned* __restrict__ keys,

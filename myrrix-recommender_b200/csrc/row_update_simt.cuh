@@ -50,6 +50,18 @@ struct RowUpdateParams {
   // with skewed row lengths (power-law data) the long rows must start first, or the CTA that meets
   // one last decides the kernel's tail.
   const int* row_order;
+  // Long rows split into chunks (tensor-core kernel only; nullptr: none).  The kernel then walks
+  // VIRTUAL rows (row_ptr / n_rows describe them): vrow[v] = the row a virtual row belongs to,
+  // vacc[v] = -1 for a whole row, else the index of the row's accumulation record
+  // (gacc[vacc * (slot floats + KS)]: the chunks' partial -D and rhs are added there; gcount counts the
+  // chunks that arrived; the last one assembles W_u with G and lambda alpha n_u -- n_u from real_ptr -- and
+  // solves).  acc_chunks[a] = chunks of record a.
+  const int* vrow;
+  const int* vacc;
+  const int* acc_chunks;
+  const long long* real_ptr;
+  float* gacc;
+  int* gcount;
   // Solve rows without entries too (W_u = G, b_u = 0): set for the list of rows that are keys
   // of the reference's map but whose entries were all pruned (InputFilesReader.java:202-211).
   int solve_empty;

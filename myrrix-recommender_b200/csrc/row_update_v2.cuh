@@ -859,13 +859,18 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
         if (mypos < p.n_rows) {
           const long long myrow = p.row_order ? (long long)p.row_order[mypos] : mypos;
           cnt_l = (int)(p.row_ptr[myrow + 1] - p.row_ptr[myrow]);
+          if (p.vacc && p.vacc[myrow] >= 0) cnt_l = -cnt_l;  // a chunk of a split row (never empty)
         }
       }
       const long long left = (p.n_rows - rb + row_step - 1) / row_step;
       const int nb = left < 32 ? (int)left : 32;
       for (int ib = 0; ib < nb; ib++) {
-        const int cnt = __shfl_sync(kFull, cnt_l, ib);
-        if (cnt == 0) continue;
+        const int cnt_s = __shfl_sync(kFull, cnt_l, ib);
+        if (cnt_s == 0) continue;
+        // chunks hand over their partial -D only: G and lambda alpha n_u are added once, by the warp
+        // that assembles the row
+        const bool is_chunk = cnt_s < 0;
+        const int cnt = is_chunk ? -cnt_s : cnt_s;
         const int nst = (cnt + E - 1) / E;
         const int nseg = (nst + kSegStages - 1) / kSegStages;
         const int ws = useq % kWSlots;
@@ -901,14 +906,18 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
             // wv[4i+0..1]: row g, columns 8i+2t, +1; wv[4i+2..3]: row g+8
             const int boff = WP::panel_off(fc) + 16 * (qd - fc) * kPS + cfr_base;
             float2 o[4];
+            const bool from_zero = is_chunk && seg == 0;  // warp-uniform
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-              const float2 n0 = *reinterpret_cast<const float2*>(src + boff + ((cfr_chunk ^ (2 * i)) << 2));
-              const float2 n1 = *reinterpret_cast<const float2*>(src + boff + 8 * kPS + ((cfr_chunk ^ (2 * i)) << 2));
+              float2 n0 = make_float2(0.f, 0.f), n1 = make_float2(0.f, 0.f);
+              if (!from_zero) {
+                n0 = *reinterpret_cast<const float2*>(src + boff + ((cfr_chunk ^ (2 * i)) << 2));
+                n1 = *reinterpret_cast<const float2*>(src + boff + 8 * kPS + ((cfr_chunk ^ (2 * i)) << 2));
+              }
               o[2 * i] = make_float2(n0.x - wv[4 * i], n0.y - wv[4 * i + 1]);
               o[2 * i + 1] = make_float2(n1.x - wv[4 * i + 2], n1.y - wv[4 * i + 3]);
             }
-            if (fc == qd && seg == 0 && has_diag) {
+            if (fc == qd && seg == 0 && has_diag && !is_chunk) {
               // diagonal entries: row g at column g (i = 0), row g+8 at column g+8 (i = 1)
               if (g & 1) { o[0].y -= lam0; o[3].y -= lam1; }
               else { o[0].x -= lam0; o[3].x -= lam1; }
@@ -957,7 +966,9 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
         if (cnt == 0) continue;
         if (useq % kCholWarps != cw) { useq++; continue; }
         const long long pos = rb + ib * row_step;
-        const long long row = p.row_order ? (long long)__ldg(p.row_order + pos) : pos;
+        const long long vr = p.row_order ? (long long)__ldg(p.row_order + pos) : pos;  // (virtual) row walked
+        const long long row = p.vrow ? (long long)__ldg(p.vrow + vr) : vr;             // the row it belongs to
+        const int acc = p.vacc ? __ldg(p.vacc + vr) : -1;
         const int nst = (cnt + E - 1) / E;
         const int smod = __shfl_sync(kFull, smod_l, ib);
         const int bs = useq % kBSlots;
@@ -1008,6 +1019,33 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
 #endif
         if (lane == 0) bulk_wait_group_read0();  // the previous row's bulk stores have read the scratch vector
         __syncwarp();
+        if (acc >= 0) {
+          // a chunk of a split row: add my partial -D and rhs to the row's record; whoever arrives last
+          // assembles N = -(G + lambda alpha n_u I) + sum of the partials and solves
+          float* ga = p.gacc + (size_t)acc * (size_t)(WP::kFloats + KS);
+          for (int e = lane; e < WP::kFloats; e += 32) atomicAdd(ga + e, slot[e]);
+#pragma unroll
+          for (int s = 0; s < CB::kS; s++) atomicAdd(ga + WP::kFloats + lane + 32 * s, b[s]);
+          __threadfence();
+          __syncwarp();
+          int arrived = 0;
+          if (lane == 0) arrived = atomicAdd(p.gcount + acc, 1);
+          arrived = __shfl_sync(kFull, arrived, 0);
+          if (arrived != __ldg(p.acc_chunks + acc) - 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&w_empty[ws]);
+            useq++;
+            continue;
+          }
+          __threadfence();
+          const float lam_n = (float)(p.lambda_alpha * (double)(p.real_ptr[row + 1] - p.real_ptr[row]));
+          for (int e = lane; e < WP::kFloats; e += 32) slot[e] = ng[e] + __ldcg(ga + e);
+          __syncwarp();
+          for (int i = lane; i < KS; i += 32) slot[WP::at(i, i)] -= (i < k) ? lam_n : 1.f;
+#pragma unroll
+          for (int s = 0; s < CB::kS; s++) b[s] = __ldcg(ga + WP::kFloats + lane + 32 * s);
+          __syncwarp();
+        }
         const float dmax = CB::diag_max(slot, lane, k);
         const bool ok = CB::factor_solve(slot, scratch, b, dmax, p.threshold, kCondLimit, lane, k);
 #ifdef ALS_PROFILE_WAITS

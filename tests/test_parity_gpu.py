@@ -227,6 +227,37 @@ def test_warp_role_mixes(M, O, monkeypatch, mix, k):
         assert fro <= TOL and mx <= TOL, (mix, k, fro, mx)
 
 
+@pytest.mark.parametrize("limit", ["64", "200", "1000"])
+@pytest.mark.parametrize("k", [32, 64, 50])
+def test_long_rows_split_into_chunks(M, O, monkeypatch, limit, k):
+    """Rows of more than MYRRIX_ALS_SPLIT_ROWS entries are walked as several virtual rows by the
+    tensor-core kernel (partial -D and rhs summed in a per-row record, the last chunk to arrive
+    assembles W_u and solves): the result is the one of the whole row.  The limit is forced low here
+    so that ragged rows of 65..3000 entries split into 2..47 chunks, next to whole rows, in both halves."""
+    monkeypatch.setenv("MYRRIX_ALS_SPLIT_ROWS", limit)
+    rng = np.random.default_rng(5 + k)
+    n_items = 900
+    lens = np.concatenate([[1, 2, 63, 64, 65, 97, 128, 129, 199, 200, 201, 257, 900, 3000 % 900 + 300],
+                           np.minimum(900, (rng.pareto(1.1, 700) * 8 + 1).astype(int))])
+    ptr, idx, val = [0], [], []
+    for n in lens:
+        idx += list(np.sort(rng.choice(n_items, size=n, replace=False)))
+        v = rng.integers(1, 6, size=n).astype(np.float32)
+        v[rng.random(n) < 0.05] *= -1
+        val += list(v)
+        ptr.append(len(idx))
+    ptr, idx, val = np.array(ptr, np.int64), np.array(idx, np.int32), np.array(val, np.float32)
+    d = rng.standard_normal((n_items, k))
+    Y0 = (d / np.sqrt((d * d).sum(1))[:, None]).astype(np.float32)
+    Xo, Yo, _, _ = O.als_run(ptr, idx, val, n_items, Y0, max_iterations=3,
+                             convergence_threshold=1e-12, n_threads=8)
+    X, Y, used = _run_gpu(M, ptr, idx, val, n_items, Y0, 3, kernel=2)
+    assert used == 2
+    for a, b in ((X, Xo), (Y, Yo)):
+        fro, mx = rel_err(a, b)
+        assert fro <= TOL and mx <= TOL, (limit, k, fro, mx)
+
+
 def test_csv_files_to_factors(M, O):
     """The step in front of the path joined to it: CSV lines with duplicates,
     deletions, near-zero sums and comments -> libmyrrix_ingest.so -> als_set_interactions ->
