@@ -38,13 +38,16 @@ CONFIGS = {
     # on one GPU and at k=64 (the tensor-core path; k=128 runs on the CUDA-core kernel): rows from 20 to
     # 20 000 entries, a few items that nearly every user has.  Device-resident line only (no CPU arm).
     "c5p": dict(users=2_000_000, items=200_000, nnz_per_user=200, k=64, powerlaw=True, max_nnz=20_000),
+    # BASELINE.json configs[4] at full size: needs --gpus 8 (10^10 entries; k = 128 runs on the CUDA-core kernel)
+    "c5": dict(users=50_000_000, items=5_000_000, nnz_per_user=200, k=128, powerlaw=True, max_nnz=20_000),
 }
 WORKLOAD_NAMES = {
     "c1": "10k x 2k, 20 nnz/user, k=16",
     "c2": "1M x 100k, 50 nnz/user, k=32",
     "c3": "10M x 1M, 100 nnz/user, k=64 (headline)",
     "c3p": "2M x 200k, 100 nnz/user, k=64 (1/5-scale headline, profiling only)",
-    "c5p": "2M x 200k, ~200 nnz/user power-law (max 20000), Zipf items, k=64 (config 5 at 1/25 scale, one GPU)",
+    "c5p": "2M x 200k, ~200 nnz/user power-law (max 20000), Zipf items, k=64 (config 5 at 1/25 scale)",
+    "c5": "50M x 5M, ~200 nnz/user power-law (max 20000), Zipf items, k=128 (config 5, 8 GPUs)",
 }
 
 
@@ -287,6 +290,19 @@ def sampled_parity(als, cfg, rank, world, n_user_rows=200, n_item_rows=50):
     als.sync()
     ib, ie = local_block(I, rank, world)
     loc = np.sort(rng.choice(ie - ib, min(n_item_rows, ie - ib), replace=False))
+    if cfg.get("powerlaw"):
+        # plus three popular items of this block (Zipf ranks >= 40 / 400 / 2500: rows of ~10^6 .. 10^4
+        # entries, which the tensor-core kernel walks in chunks) -- a uniform sample rarely meets one
+        from oracle import synth
+        _, mul, add = synth.powerlaw_params(I, cfg["nnz_per_user"], cfg["max_nnz"], SEED)
+        extra = []
+        for t in (40, 400, 2500):
+            for r in range(t, min(t + 64 * world, I)):
+                item = (mul * r + add) % I
+                if ib <= item < ie:
+                    extra.append(item - ib)
+                    break
+        loc = np.unique(np.concatenate([loc, np.array(extra, dtype=loc.dtype)]))
     ip, ii, iv = rows_csr(loc, True)
     users, inv = np.unique(ii, return_inverse=True)
     Xc = als.get_rows(0, users)
@@ -353,11 +369,14 @@ def main():
         als.comm_init(rank, world, uid[0])
     dbg("comm ready, synthesising")
     if cfg.get("powerlaw"):
-        if world > 1:
-            raise SystemExit("the power-law generator fills single-GPU handles (config c5p: --gpus 1)")
         args.no_e2e = args.no_cpu_baseline = True
         als.synth_interactions_powerlaw(U, I, nnz_pu, max_nnz=cfg["max_nnz"], seed=SEED, neg_fraction=0.0)
-        nnz = int(als.info().nnz)
+        nnz = int(als.info().nnz)  # this rank's user block
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([nnz], device="cuda", dtype=torch.int64)
+            dist.all_reduce(t)
+            nnz = int(t.item())
     else:
         als.synth_interactions(U, I, nnz_pu, seed=SEED, neg_fraction=0.0)
     als.synth_y0(seed=SEED)

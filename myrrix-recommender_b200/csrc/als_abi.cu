@@ -1814,50 +1814,107 @@ static unsigned long long gcd_u64(unsigned long long a, unsigned long long b) {
   return a;
 }
 
-int als_synth_interactions_powerlaw(als_handle* h, int64_t n_users, int64_t n_items, double mean_nnz,
-                                    int32_t max_nnz, uint64_t seed, double neg_fraction) {
-  if (!h) return ALS_E_ARG;
-  if (!(mean_nnz >= 1.0) || max_nnz < 2 || n_items < 1) return fail(h, ALS_E_ARG, "bad power-law parameters");
-  if (neg_fraction < 0.0 || neg_fraction > 1.0) return fail(h, ALS_E_ARG, "bad neg_fraction");
-  if (h->world > 1) return fail(h, ALS_E_UNSUPPORTED, "the power-law generator fills single-GPU handles");
-  CU(h, cudaSetDevice(h->device));
-  int rc = set_dims(h, n_users, n_items);
-  if (rc != ALS_OK) return rc;
-  Csr& A = h->by_user;
-  free_csr(h, &A);
-  h->have_by_item = false;
-  if ((rc = reset_for_new_interactions(h)) != ALS_OK) return rc;
+// rows [row_begin, row_begin + rows) of the power-law workload into `out` (see aux_kernels.cuh)
+static int powerlaw_block(als_handle* h, long long row_begin, long long rows, int64_t n_items, double mean_nnz,
+                          int32_t max_nnz, uint64_t seed, double neg_fraction, Csr* out) {
+  Csr& A = *out;
   // E[x] of the truncated law = ln(n_max) n_max / (n_max - 1): scale the draw so the mean is mean_nnz
   const double ex = log((double)max_nnz) * (double)max_nnz / ((double)max_nnz - 1.0);
   const double scale = mean_nnz / ex;
   unsigned long long mul = (mix64(seed ^ 0x2545f4914f6cdd1dULL) % (unsigned long long)n_items) | 1ULL;
   while (gcd_u64(mul, (unsigned long long)n_items) != 1ULL) mul += 2ULL;
   const unsigned long long add = mix64(seed ^ 0x9e3779b97f4a7c15ULL) % (unsigned long long)n_items;
-  A.rows = n_users;
-  A.row_begin = 0;
+  A.rows = rows;
+  A.row_begin = row_begin;
+  int rc;
   long long* counts = nullptr;
-  if ((rc = dev_alloc(h, &counts, (size_t)n_users + 1)) != ALS_OK) return rc;
-  if ((rc = dev_alloc(h, &A.ptr, (size_t)n_users + 1)) != ALS_OK) return rc;
-  powerlaw_counts_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(0, n_users, n_items, scale, max_nnz, seed, counts);
+  if ((rc = dev_alloc(h, &counts, (size_t)rows + 1)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &A.ptr, (size_t)rows + 1)) != ALS_OK) return rc;
+  powerlaw_counts_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(row_begin, rows, n_items, scale, max_nnz, seed, counts);
   {
     void* stmp = nullptr;
     size_t sbytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, sbytes, counts, A.ptr, (int)(n_users + 1), h->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, sbytes, counts, A.ptr, (int)(rows + 1), h->stream);
     CU(h, cudaMalloc(&stmp, sbytes ? sbytes : 1));
-    cub::DeviceScan::ExclusiveSum(stmp, sbytes, counts, A.ptr, (int)(n_users + 1), h->stream);
+    cub::DeviceScan::ExclusiveSum(stmp, sbytes, counts, A.ptr, (int)(rows + 1), h->stream);
     CU(h, cudaStreamSynchronize(h->stream));
     cudaFree(stmp);
   }
-  dev_free(h, &counts, (size_t)n_users + 1);
-  CU(h, cudaMemcpy(&A.nnz, A.ptr + n_users, sizeof(long long), cudaMemcpyDeviceToHost));
+  dev_free(h, &counts, (size_t)rows + 1);
+  CU(h, cudaMemcpy(&A.nnz, A.ptr + rows, sizeof(long long), cudaMemcpyDeviceToHost));
   if ((rc = dev_alloc(h, &A.idx, (size_t)A.nnz)) != ALS_OK) return rc;
   if ((rc = dev_alloc(h, &A.val, (size_t)A.nnz)) != ALS_OK) return rc;
   const unsigned int thr = (unsigned int)(neg_fraction * 16777216.0);
-  powerlaw_rows_kernel<<<h->sm_count * 8, 128, 0, h->stream>>>(0, n_users, n_items, seed, thr, mul, add, A.ptr, A.idx,
-                                                                A.val);
+  powerlaw_rows_kernel<<<h->sm_count * 8, 128, 0, h->stream>>>(row_begin, rows, n_items, seed, thr, mul, add, A.ptr,
+                                                                A.idx, A.val);
   h->launches += 3;
   CU(h, cudaGetLastError());
-  return build_transpose(h);
+  return ALS_OK;
+}
+
+// the entries of A whose column lies in [lo, hi), rows kept (A's row order and row_begin)
+static int filter_columns(als_handle* h, const Csr& A, long long lo, long long hi, Csr* out) {
+  Csr& T = *out;
+  T.rows = A.rows;
+  T.row_begin = A.row_begin;
+  int rc;
+  long long* counts = nullptr;
+  if ((rc = dev_alloc(h, &counts, (size_t)A.rows + 1)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &T.ptr, (size_t)A.rows + 1)) != ALS_OK) return rc;
+  filter_columns_kernel<<<h->sm_count * 8, 128, 0, h->stream>>>(A.ptr, A.rows, A.idx, A.val, (int)lo, (int)hi, counts,
+                                                                 nullptr, nullptr, nullptr);
+  {
+    void* stmp = nullptr;
+    size_t sbytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, sbytes, counts, T.ptr, (int)(A.rows + 1), h->stream);
+    CU(h, cudaMalloc(&stmp, sbytes ? sbytes : 1));
+    cub::DeviceScan::ExclusiveSum(stmp, sbytes, counts, T.ptr, (int)(A.rows + 1), h->stream);
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(stmp);
+  }
+  dev_free(h, &counts, (size_t)A.rows + 1);
+  CU(h, cudaMemcpy(&T.nnz, T.ptr + A.rows, sizeof(long long), cudaMemcpyDeviceToHost));
+  if ((rc = dev_alloc(h, &T.idx, (size_t)T.nnz)) != ALS_OK) return rc;
+  if ((rc = dev_alloc(h, &T.val, (size_t)T.nnz)) != ALS_OK) return rc;
+  filter_columns_kernel<<<h->sm_count * 8, 128, 0, h->stream>>>(A.ptr, A.rows, A.idx, A.val, (int)lo, (int)hi, nullptr,
+                                                                 T.ptr, T.idx, T.val);
+  h->launches += 3;
+  CU(h, cudaGetLastError());
+  return ALS_OK;
+}
+
+int als_synth_interactions_powerlaw(als_handle* h, int64_t n_users, int64_t n_items, double mean_nnz,
+                                    int32_t max_nnz, uint64_t seed, double neg_fraction) {
+  if (!h) return ALS_E_ARG;
+  if (!(mean_nnz >= 1.0) || max_nnz < 2 || n_items < 1) return fail(h, ALS_E_ARG, "bad power-law parameters");
+  if (neg_fraction < 0.0 || neg_fraction > 1.0) return fail(h, ALS_E_ARG, "bad neg_fraction");
+  CU(h, cudaSetDevice(h->device));
+  int rc = set_dims(h, n_users, n_items);
+  if (rc != ALS_OK) return rc;
+  // Sharded: every rank draws its own user block (the generator is counter-based: a row depends on
+  // its global index only).  The item permutation spreads the popular items over the item blocks.
+  long long ub, ue, ib, ie;
+  local_block(h, h->n_users, &ub, &ue);
+  local_block(h, h->n_items, &ib, &ie);
+  free_csr(h, &h->by_user);
+  h->have_by_item = false;
+  if ((rc = reset_for_new_interactions(h)) != ALS_OK) return rc;
+  if ((rc = powerlaw_block(h, ub, ue - ub, n_items, mean_nnz, max_nnz, seed, neg_fraction, &h->by_user)) != ALS_OK) return rc;
+  if (h->world == 1) return build_transpose(h);
+  // with a communicator the by-item blocks are exchanged on the devices
+  if (h->comm) return build_by_item_distributed(h);
+  // partition-only handle (no communicator): re-draw every user, keep my item block, transpose
+  Csr all, mine;
+  if ((rc = powerlaw_block(h, 0, n_users, n_items, mean_nnz, max_nnz, seed, neg_fraction, &all)) == ALS_OK &&
+      (rc = filter_columns(h, all, ib, ie, &mine)) == ALS_OK) {
+    free_csr(h, &all);
+    rc = build_transpose_from(h, mine, ib, ie - ib, &h->by_item);
+  }
+  free_csr(h, &all);
+  free_csr(h, &mine);
+  if (rc != ALS_OK) return rc;
+  h->have_by_item = true;
+  return ALS_OK;
 }
 
 int als_synth_y0(als_handle* h, uint64_t seed) {

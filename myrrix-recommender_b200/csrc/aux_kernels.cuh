@@ -149,6 +149,32 @@ __global__ void split_fill_kernel(const long long* __restrict__ ptr, long long n
   }
 }
 
+// Entries of a CSR whose column lies in [lo, hi): first call (counts != nullptr) counts them per row,
+// second call (optr = exclusive sum of the counts) copies them, order kept.
+__global__ void filter_columns_kernel(const long long* __restrict__ ptr, long long n_rows, const int* __restrict__ idx,
+                                      const float* __restrict__ val, int lo, int hi, long long* __restrict__ counts,
+                                      const long long* __restrict__ optr, int* __restrict__ oidx,
+                                      float* __restrict__ oval) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r <= n_rows; r += stride) {
+    if (r == n_rows) {
+      if (counts) counts[r] = 0;
+      continue;
+    }
+    long long o = counts ? 0 : optr[r];
+    for (long long e = ptr[r]; e < ptr[r + 1]; e++) {
+      const int c = idx[e];
+      if (c < lo || c >= hi) continue;
+      if (!counts) {
+        oidx[o] = c;
+        oval[o] = val[e];
+      }
+      o++;
+    }
+    if (counts) counts[r] = o;
+  }
+}
+
 // keys[r] = entries of row r, vals[r] = r: sorted by key, descending, they give the visiting order of
 // the row updates (longest rows first)
 __global__ void row_length_keys_kernel(const long long* __restrict__ ptr, long long n_rows, unsigned* __restrict__ keys,

@@ -428,6 +428,28 @@ def test_sharded_synthesis_matches_slices_of_the_whole(M, O):
             assert np.array_equal(Y[:ib], Y0[:ib]) and np.array_equal(Y[ie:], Y0[ie:])
 
 
+def test_sharded_powerlaw_synthesis_matches_slices_of_the_twin(M, O):
+    """The power-law generator on sharded handles (partition-only here: one GPU): every rank's by-user
+    block and by-item block equal the slices of oracle/synth.py's matrix."""
+    from myrrix_recommender_b200 import sharding as S
+    from oracle import synth
+    U, I, k, world = 3001, 457, 32, 3
+    ptr, idx, val = synth.synth_rows_powerlaw(0, U, I, 25, max_nnz=400, seed=99, neg_fraction=0.05)
+    with M.NativeALS(k) as whole:
+        whole.set_interactions(U, I, ptr, idx, val)
+        cptr, cidx, cval = whole.get_interactions(by_column=True)
+    for rank in range(world):
+        with M.NativeALS(k) as als:
+            als.comm_init(rank, world, None)
+            als.synth_interactions_powerlaw(U, I, 25, max_nnz=400, seed=99, neg_fraction=0.05)
+            p, i, v = als.get_interactions()
+            ep, ei, ev = S.shard_rows(ptr, idx, val, rank, world)
+            assert np.array_equal(p, ep) and np.array_equal(i, ei) and np.array_equal(v, ev)
+            p, i, v = als.get_interactions(by_column=True)
+            ep, ei, ev = S.shard_rows(cptr, cidx, cval, rank, world)
+            assert np.array_equal(p, ep) and np.array_equal(i, ei) and np.array_equal(v, ev)
+
+
 def test_build_then_fold_in(M, O):
     """The step after the path: a model build on the GPU, X'X and Y'Y from the
     resident factors (als_gramian), then online writes folded in by libmyrrix_foldin.so --
