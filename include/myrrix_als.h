@@ -201,7 +201,8 @@ typedef struct als_timings {
   double update_y_ms;       /* row-update kernel over items, summed */
   double exchange_ms;       /* multi-GPU factor exchange, summed */
   int32_t n_half_x, n_half_y;
-  int64_t fp64_retry_rows;  /* rows the fp32 tensor-core path handed to the fp64 kernel */
+  int64_t fp64_retry_rows;  /* rows the fp32 tensor-core path handed to the fp64 kernels */
+  int64_t fp64_resolve_rows; /* of those: solved in fp64 from the stashed data term, without gathering the row again */
 } als_timings;
 int als_profile_enable(als_handle *h, int32_t on);
 int als_get_timings(als_handle *h, als_timings *out, int32_t reset);
@@ -216,7 +217,7 @@ int als_synth_interactions(als_handle *h, int64_t n_users, int64_t n_items, int3
 /* Power-law variant: entries per user from a truncated power law (density
  * ~ x^-2 on [1, max_nnz], scaled to a mean of about mean_nnz, at least one), item popularity
  * Zipf(s = 1) over a pseudo-random permutation of the items, no item twice per user; strengths as
- * above.  Single-GPU handles only. */
+ * above.  Sharded handles draw their own user block (the by-item blocks are exchanged on the devices). */
 int als_synth_interactions_powerlaw(als_handle *h, int64_t n_users, int64_t n_items, double mean_nnz,
                                     int32_t max_nnz, uint64_t seed, double neg_fraction);
 /* Y0: every row k i.i.d. N(0,1) normalised to unit L2 norm in fp32 (the distribution of

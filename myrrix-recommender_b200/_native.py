@@ -35,7 +35,7 @@ class AlsTimings(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("launches", C.c_int32), ("gramian_ms", C.c_double),
                 ("update_x_ms", C.c_double), ("update_y_ms", C.c_double),
                 ("exchange_ms", C.c_double), ("n_half_x", C.c_int32), ("n_half_y", C.c_int32),
-                ("fp64_retry_rows", C.c_int64)]
+                ("fp64_retry_rows", C.c_int64), ("fp64_resolve_rows", C.c_int64)]
 
 
 # Every symbol include/myrrix_als.h declares: (name, restype, argtypes)

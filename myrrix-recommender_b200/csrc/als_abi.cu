@@ -20,6 +20,7 @@
 #include "row_update_simt.cuh"
 #include "row_update_umma.cuh"
 #include "row_update_v2.cuh"
+#include "resolve_fp64.cuh"
 #include <nvtx3/nvToolsExt.h>
 
 using namespace als;
@@ -112,6 +113,20 @@ struct als_handle {
     size_t acc_floats = 0;   // floats of one accumulation record
   } split[2];
   long long split_limit = 8192;  // entries; MYRRIX_ALS_SPLIT_ROWS (0: never split)
+  // stash mode of the tensor-core kernel (RowUpdateParams::stash), per orientation: switched on when the
+  // previous launch of the same half handed many rows to the fp64 paths, off again when it no longer does
+  int stash_policy = -1;          // MYRRIX_ALS_STASH: 0 never, 1 always, unset: by the previous launch's count
+  bool stash_on[2] = {false, false};
+  bool fail_pending[2] = {false, false};
+  cudaEvent_t fail_ev[2] = {nullptr, nullptr};
+  int* h_fail = nullptr;          // pinned: [which][retry count, resolve count] of the last launch
+  float* d_stash = nullptr;       // [CTA][solving warp][record]
+  size_t stash_floats = 0;
+  float* d_resolve_buf = nullptr;
+  int* d_resolve_rows = nullptr;
+  int* d_resolve_count = nullptr;
+  long long resolve_cap = 0;
+  size_t resolve_rec = 0;         // floats per record
   // fold-in solver state of the generation (als_set_fold_in_state): [0] X'X, [1] Y'Y
   double* fi_qrt[2] = {nullptr, nullptr};
   double* fi_rdiag[2] = {nullptr, nullptr};
@@ -556,12 +571,16 @@ int configure_kernels(als_handle* h) {
     if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<32, 4>, umma::Smem<32, 4>::kTotal)) != ALS_OK) return rc;
     if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<32, 8>, umma::Smem<32, 8>::kTotal)) != ALS_OK) return rc;
     if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<32, v2::Mixes<32>::Long>, v2::Smem<32, v2::Mixes<32>::Long>::kTotal)) != ALS_OK) return rc;
+    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<32, v2::Mixes<32>::Long, true>, v2::Smem<32, v2::Mixes<32>::Long>::kTotal)) != ALS_OK) return rc;
     if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<32, v2::Mixes<32>::Short>, v2::Smem<32, v2::Mixes<32>::Short>::kTotal)) != ALS_OK) return rc;
+    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<32, v2::Mixes<32>::Short, true>, v2::Smem<32, v2::Mixes<32>::Short>::kTotal)) != ALS_OK) return rc;
   } else if (h->ks == 64) {
     if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<64, 4>, umma::Smem<64, 4>::kTotal)) != ALS_OK) return rc;
     if ((rc = set_smem_attr(h, umma::row_update_umma_kernel<64, 8>, umma::Smem<64, 8>::kTotal)) != ALS_OK) return rc;
     if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<64, v2::MixLong>, v2::Smem<64, v2::MixLong>::kTotal)) != ALS_OK) return rc;
+    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<64, v2::MixLong, true>, v2::Smem<64, v2::MixLong>::kTotal)) != ALS_OK) return rc;
     if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<64, v2::MixShort>, v2::Smem<64, v2::MixShort>::kTotal)) != ALS_OK) return rc;
+    if ((rc = set_smem_attr(h, v2::row_update_v2_kernel<64, v2::MixShort, true>, v2::Smem<64, v2::MixShort>::kTotal)) != ALS_OK) return rc;
   }
   return ALS_OK;
 }
@@ -599,6 +618,47 @@ int ensure_row_order(als_handle* h, const Csr& R, int which) {
   h->launches += 2;
   if (e != cudaSuccess) return fail(h, ALS_E_CUDA, "row order sort: %s", cudaGetErrorString(e));
   h->order_valid[which] = true;
+  return ALS_OK;
+}
+
+// Stash mode for the coming launch of orientation `which` (see RowUpdateParams::stash): decided from the
+// number of rows the previous launch of the same half handed to the fp64 paths (known by now: at least
+// one other launch has been queued since), with hysteresis; buffers are created on first use.
+int prepare_stash(als_handle* h, const Csr& R, int which) {
+  if (h->stash_policy >= 0) {
+    h->stash_on[which] = h->stash_policy == 1;
+  } else if (h->fail_pending[which]) {
+    CU(h, cudaEventSynchronize(h->fail_ev[which]));
+    h->fail_pending[which] = false;
+    const long long fails = (long long)h->h_fail[2 * which] + (long long)h->h_fail[2 * which + 1];
+    const long long on_at = R.rows / 64 > 256 ? R.rows / 64 : 256;
+    if (!h->stash_on[which] && fails >= on_at) h->stash_on[which] = true;
+    else if (h->stash_on[which] && fails < on_at / 4) h->stash_on[which] = false;
+  }
+  if (!h->stash_on[which]) return ALS_OK;
+  int rc;
+  const size_t rec = (h->ks == 64 ? (size_t)WPanels<64>::kFloats : (size_t)WPanels<32>::kFloats) + (size_t)h->ks;
+  const size_t stash_floats = (size_t)h->sm_count * 16 * rec;  // (at most 16 solving warps per CTA)
+  if (!h->d_stash || h->stash_floats < stash_floats) {
+    dev_free(h, &h->d_stash, h->stash_floats);
+    h->stash_floats = 0;
+    if ((rc = dev_alloc(h, &h->d_stash, stash_floats)) != ALS_OK) return rc;
+    h->stash_floats = stash_floats;
+  }
+  if (!h->d_resolve_count && (rc = dev_alloc(h, &h->d_resolve_count, 1)) != ALS_OK) return rc;
+  // records for every row, up to 2 GB (rows beyond that take the retry list)
+  long long cap = (long long)((2ULL << 30) / (rec * sizeof(float)));
+  if (cap > R.rows) cap = R.rows;
+  if (cap < 1) cap = 1;
+  if (h->resolve_cap < cap || h->resolve_rec != rec) {
+    dev_free(h, &h->d_resolve_buf, (size_t)h->resolve_cap * h->resolve_rec);
+    dev_free(h, &h->d_resolve_rows, (size_t)h->resolve_cap);
+    h->resolve_cap = 0;
+    if ((rc = dev_alloc(h, &h->d_resolve_buf, (size_t)cap * rec)) != ALS_OK) return rc;
+    if ((rc = dev_alloc(h, &h->d_resolve_rows, (size_t)cap)) != ALS_OK) return rc;
+    h->resolve_cap = cap;
+    h->resolve_rec = rec;
+  }
   return ALS_OK;
 }
 
@@ -760,7 +820,24 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
       }
     }
     const CUtensorMap& tm = h->gather_map[mi];
-    const RowUpdateParams p_rows = p;  // the rows as stored: what the fp64 re-solve below walks
+    p.stash = nullptr;
+    p.resolve_buf = nullptr;
+    p.resolve_rows = nullptr;
+    p.resolve_count = nullptr;
+    p.resolve_cap = 0;
+    if (v2_kernel) {
+      const int src = prepare_stash(h, R, which);
+      if (src != ALS_OK) { nvtxRangePop(); return src; }
+      if (h->stash_on[which]) {
+        p.stash = h->d_stash;
+        p.resolve_buf = h->d_resolve_buf;
+        p.resolve_rows = h->d_resolve_rows;
+        p.resolve_count = h->d_resolve_count;
+        p.resolve_cap = (int)h->resolve_cap;
+        cudaMemsetAsync(h->d_resolve_count, 0, sizeof(int), h->stream);
+      }
+    }
+    const RowUpdateParams p_rows = p;  // the rows as stored: what the fp64 re-solves below walk
     if (sp) {
       p.row_ptr = sp->vptr;
       p.n_rows = sp->n_virtual;
@@ -772,12 +849,21 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
       cudaMemsetAsync(sp->gacc, 0, (size_t)sp->n_acc * sp->acc_floats * sizeof(float), h->stream);
       cudaMemsetAsync(sp->gcount, 0, (size_t)sp->n_acc * sizeof(int), h->stream);
     }
+    const bool ext = sp != nullptr || p.stash != nullptr;  // virtual rows / stash mode: the extended variant
     if (h->ks == 64 && !h->legacy_umma) {
-      rc = long_rows ? launch_row_update_v2_t<64, v2::MixLong>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err))
-                     : launch_row_update_v2_t<64, v2::MixShort>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err));
+      if (ext)
+        rc = long_rows ? launch_row_update_v2_t<64, v2::MixLong, true>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err))
+                       : launch_row_update_v2_t<64, v2::MixShort, true>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err));
+      else
+        rc = long_rows ? launch_row_update_v2_t<64, v2::MixLong>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err))
+                       : launch_row_update_v2_t<64, v2::MixShort>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err));
     } else if (h->ks == 32 && !h->legacy_umma) {
-      rc = long_rows ? launch_row_update_v2_t<32, v2::Mixes<32>::Long>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err))
-                     : launch_row_update_v2_t<32, v2::Mixes<32>::Short>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err));
+      if (ext)
+        rc = long_rows ? launch_row_update_v2_t<32, v2::Mixes<32>::Long, true>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err))
+                       : launch_row_update_v2_t<32, v2::Mixes<32>::Short, true>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err));
+      else
+        rc = long_rows ? launch_row_update_v2_t<32, v2::Mixes<32>::Long>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err))
+                       : launch_row_update_v2_t<32, v2::Mixes<32>::Short>(p, tm, h->sm_count, h->stream, h->err, sizeof(h->err));
     } else {
       rc = launch_row_update_umma(h->ks, p, long_rows, h->sm_count, h->stream, h->err, sizeof(h->err));
     }
@@ -788,6 +874,28 @@ int launch_row_update(als_handle* h, const Csr& R, const float* M, float* out, i
       accumulate_count_kernel<<<1, 1, 0, h->stream>>>(h->d_retry_count, h->d_retry_total);
       h->launches += 1;
       p = p_rows;
+      if (p.stash) {
+        // rows refused in stash mode: fp64 solve from the fp64 Gramian and the stashed data term
+        accumulate_resolve_kernel<<<1, 1, 0, h->stream>>>(h->d_resolve_count, p.resolve_cap, h->d_retry_total);
+        // (latency-bound: one barrier per column; as many CTAs per SM as the 35 KB / 10 KB of shared memory allow)
+        if (h->ks == 64) resolve_fp64_kernel<64><<<h->sm_count * 6, 128, 0, h->stream>>>(p);
+        else resolve_fp64_kernel<32><<<h->sm_count * 12, 128, 0, h->stream>>>(p);
+        h->launches += 2;
+      }
+      if (v2_kernel && h->stash_policy < 0) {
+        // how many rows left the fp32 path: read before the next launch of this half (prepare_stash)
+        if (!h->h_fail) {
+          CU(h, cudaHostAlloc((void**)&h->h_fail, 4 * sizeof(int), cudaHostAllocDefault));
+          memset(h->h_fail, 0, 4 * sizeof(int));
+        }
+        if (!h->fail_ev[which]) CU(h, cudaEventCreateWithFlags(&h->fail_ev[which], cudaEventDisableTiming));
+        h->h_fail[2 * which + 1] = 0;
+        CU(h, cudaMemcpyAsync(&h->h_fail[2 * which], h->d_retry_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        if (p.stash)
+          CU(h, cudaMemcpyAsync(&h->h_fail[2 * which + 1], h->d_resolve_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaEventRecord(h->fail_ev[which], h->stream));
+        h->fail_pending[which] = true;
+      }
       RowUpdateParams q = p;
       q.row_list = h->d_retry_rows;
       q.row_list_count = h->d_retry_count;
@@ -1098,6 +1206,8 @@ int reset_for_new_interactions(als_handle* h) {
   for (int w = 0; w < 2; w++) {
     h->pe_rows[w] = 0;
     CU(h, cudaMemsetAsync(h->d_pe_count[w], 0, sizeof(int), h->stream));
+    h->stash_on[w] = false;  // (what the old interactions' launches told about the fp32 path's yield)
+    h->fail_pending[w] = false;
   }
   return ALS_OK;
 }
@@ -1210,6 +1320,7 @@ int als_create(const als_config* cfg, als_handle** out) {
   if (const char* e = getenv("MYRRIX_ALS_V1")) h->legacy_umma = atoi(e) != 0;
   if (const char* e = getenv("MYRRIX_ALS_NO_P2P")) h->p2p_disabled = atoi(e) != 0;
   if (const char* e = getenv("MYRRIX_ALS_NO_ROW_ORDER")) h->no_row_order = atoi(e) != 0;
+  if (const char* e = getenv("MYRRIX_ALS_STASH")) h->stash_policy = atoi(e) != 0 ? 1 : 0;
   if (const char* e = getenv("MYRRIX_ALS_SPLIT_ROWS")) {
     const long long v = atoll(e);
     h->split_limit = v <= 0 ? 0 : (v < 64 ? 64 : v);
@@ -1237,8 +1348,8 @@ int als_create(const als_config* cfg, als_handle** out) {
   if ((rc = dev_alloc(h, &h->d_ticket, 1)) != ALS_OK) return rc;
   if ((rc = dev_alloc(h, &h->d_rank, 1)) != ALS_OK) return rc;
   if ((rc = dev_alloc(h, &h->d_retry_count, 1)) != ALS_OK) return rc;
-  if ((rc = dev_alloc(h, &h->d_retry_total, 1)) != ALS_OK) return rc;
-  CU(h, cudaMemsetAsync(h->d_retry_total, 0, sizeof(long long), h->stream));
+  if ((rc = dev_alloc(h, &h->d_retry_total, 2)) != ALS_OK) return rc;  // [0] all fp64 rows, [1] of those: re-solved from the stash
+  CU(h, cudaMemsetAsync(h->d_retry_total, 0, 2 * sizeof(long long), h->stream));
   const size_t scratch = (size_t)2 * h->k * h->k + 2 * h->k + 1;
   if ((rc = dev_alloc(h, &h->d_scratch, scratch > 10000 ? scratch : 10000)) != ALS_OK) return rc;
   CU(h, cudaMemsetAsync(h->d_status, 0, sizeof(DeviceStatus), h->stream));
@@ -1271,10 +1382,14 @@ int als_destroy(als_handle* h) {
   // pool allocations go back to the pool (stream-ordered; nothing is unmapped)
   void* pooled[] = {h->G, h->G_partial, h->d_status, h->d_ticket, h->d_rank, h->d_scratch, h->d_retry_rows,
                     h->d_retry_count, h->d_retry_total, h->d_flag, h->d_probe_idx, h->d_probe_out,
-                    h->d_pe_rows[0], h->d_pe_rows[1], h->d_pe_count[0], h->d_pe_count[1]};
+                    h->d_pe_rows[0], h->d_pe_rows[1], h->d_pe_count[0], h->d_pe_count[1],
+                    h->d_stash, h->d_resolve_buf, h->d_resolve_rows, h->d_resolve_count};
   for (void* q : pooled)
     if (q) cudaFreeAsync(q, h->stream);
   cudaStreamSynchronize(h->stream);
+  for (int w = 0; w < 2; w++)
+    if (h->fail_ev[w]) cudaEventDestroy(h->fail_ev[w]);
+  if (h->h_fail) cudaFreeHost(h->h_fail);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return ALS_OK;
@@ -1733,15 +1848,16 @@ int als_get_timings(als_handle* h, als_timings* out, int32_t reset) {
   cudaStreamSynchronize(h->stream);
   prof_drain(h);
   h->tm.launches = h->launches;
-  long long retried = 0;
-  cudaMemcpy(&retried, h->d_retry_total, sizeof(long long), cudaMemcpyDeviceToHost);
-  h->tm.fp64_retry_rows = retried;
+  long long retried[2] = {0, 0};
+  cudaMemcpy(retried, h->d_retry_total, 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+  h->tm.fp64_retry_rows = retried[0];
+  h->tm.fp64_resolve_rows = retried[1];
   *out = h->tm;
   if (reset) {
     memset(&h->tm, 0, sizeof(h->tm));
     h->tm.struct_size = (int32_t)sizeof(als_timings);
     h->launches = 0;
-    cudaMemsetAsync(h->d_retry_total, 0, sizeof(long long), h->stream);
+    cudaMemsetAsync(h->d_retry_total, 0, 2 * sizeof(long long), h->stream);
   }
   return ALS_OK;
 }

@@ -53,6 +53,15 @@ __global__ void accumulate_count_kernel(const int* count, long long* total) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *total += (long long)*count;
 }
 
+// total[0] += records, total[1] += records: rows re-solved in fp64 from the stash (records = min(count, cap))
+__global__ void accumulate_resolve_kernel(const int* count, int cap, long long* total) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long n = *count < cap ? *count : cap;
+    total[0] += n;
+    total[1] += n;
+  }
+}
+
 __global__ void fill_ptr_zero_kernel(long long* ptr, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) ptr[i] = 0;

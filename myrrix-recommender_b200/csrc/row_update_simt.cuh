@@ -62,6 +62,18 @@ struct RowUpdateParams {
   const long long* real_ptr;
   float* gacc;
   int* gcount;
+  // Stash mode (tensor-core kernel only; nullptr: off).  For workloads where many rows fail the fp32
+  // solve's conditioning gate because G itself is ill-conditioned (power-law data): the drain hands over
+  // the data term -D alone, the solving warp keeps a copy of it (and of the rhs) in its own record of
+  // `stash` ([CTA][solving warp][slot floats + KS]) before it adds G and lambda alpha n_u in fp32, and a
+  // row that fails is appended to resolve_buf / resolve_rows (up to resolve_cap records; beyond that:
+  // the retry list) -- resolve_fp64_kernel then solves (G + D + lambda alpha n_u I) x = b in fp64 from
+  // the fp64 Gramian and the tensor-core D, without gathering the row again.
+  float* stash;
+  float* resolve_buf;
+  int* resolve_rows;
+  int* resolve_count;
+  int resolve_cap;
   // Solve rows without entries too (W_u = G, b_u = 0): set for the list of rows that are keys
   // of the reference's map but whose entries were all pruned (InputFilesReader.java:202-211).
   int solve_empty;

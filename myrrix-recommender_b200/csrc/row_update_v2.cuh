@@ -388,7 +388,10 @@ __device__ __forceinline__ void load_batch(const RowUpdateParams& p, long long r
   B.ne_mask = __ballot_sync(kFull, B.cnt > 0);
 }
 
-template <int KS, class MX>
+// kExt: the variant that walks virtual rows (long rows split into chunks) and / or runs in stash mode
+// (RowUpdateParams::vrow, ::stash).  The plain variant carries none of that code: its solving warps
+// have no registers to spare for state that uniform workloads never use.
+template <int KS, class MX, bool kExt = false>
 __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const RowUpdateParams p,
                                                                         const __grid_constant__ CUtensorMap tmapM) {
   static_assert(KS == 64 || KS == 32, "second-generation kernel: k = 32 or 64");
@@ -859,7 +862,9 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
         if (mypos < p.n_rows) {
           const long long myrow = p.row_order ? (long long)p.row_order[mypos] : mypos;
           cnt_l = (int)(p.row_ptr[myrow + 1] - p.row_ptr[myrow]);
-          if (p.vacc && p.vacc[myrow] >= 0) cnt_l = -cnt_l;  // a chunk of a split row (never empty)
+          if constexpr (kExt) {
+            if (p.vacc && p.vacc[myrow] >= 0) cnt_l = -cnt_l;  // a chunk of a split row (never empty)
+          }
         }
       }
       const long long left = (p.n_rows - rb + row_step - 1) / row_step;
@@ -869,7 +874,8 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
         if (cnt_s == 0) continue;
         // chunks hand over their partial -D only: G and lambda alpha n_u are added once, by the warp
         // that assembles the row
-        const bool is_chunk = cnt_s < 0;
+        const bool is_chunk = kExt && cnt_s < 0;
+        const bool no_g = kExt && (is_chunk || p.stash != nullptr);  // (stash mode: the solving warp adds them, see below)
         const int cnt = is_chunk ? -cnt_s : cnt_s;
         const int nst = (cnt + E - 1) / E;
         const int nseg = (nst + kSegStages - 1) / kSegStages;
@@ -906,7 +912,7 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
             // wv[4i+0..1]: row g, columns 8i+2t, +1; wv[4i+2..3]: row g+8
             const int boff = WP::panel_off(fc) + 16 * (qd - fc) * kPS + cfr_base;
             float2 o[4];
-            const bool from_zero = is_chunk && seg == 0;  // warp-uniform
+            const bool from_zero = no_g && seg == 0;  // warp-uniform
 #pragma unroll
             for (int i = 0; i < 2; i++) {
               float2 n0 = make_float2(0.f, 0.f), n1 = make_float2(0.f, 0.f);
@@ -917,7 +923,7 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
               o[2 * i] = make_float2(n0.x - wv[4 * i], n0.y - wv[4 * i + 1]);
               o[2 * i + 1] = make_float2(n1.x - wv[4 * i + 2], n1.y - wv[4 * i + 3]);
             }
-            if (fc == qd && seg == 0 && has_diag && !is_chunk) {
+            if (fc == qd && seg == 0 && has_diag && !no_g) {
               // diagonal entries: row g at column g (i = 0), row g+8 at column g+8 (i = 1)
               if (g & 1) { o[0].y -= lam0; o[3].y -= lam1; }
               else { o[0].x -= lam0; o[3].x -= lam1; }
@@ -967,8 +973,12 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
         if (useq % kCholWarps != cw) { useq++; continue; }
         const long long pos = rb + ib * row_step;
         const long long vr = p.row_order ? (long long)__ldg(p.row_order + pos) : pos;  // (virtual) row walked
-        const long long row = p.vrow ? (long long)__ldg(p.vrow + vr) : vr;             // the row it belongs to
-        const int acc = p.vacc ? __ldg(p.vacc + vr) : -1;
+        long long row = vr;  // the row it belongs to
+        int acc = -1;
+        if constexpr (kExt) {
+          if (p.vrow) row = (long long)__ldg(p.vrow + vr);
+          if (p.vacc) acc = __ldg(p.vacc + vr);
+        }
         const int nst = (cnt + E - 1) / E;
         const int smod = __shfl_sync(kFull, smod_l, ib);
         const int bs = useq % kBSlots;
@@ -1019,13 +1029,17 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
 #endif
         if (lane == 0) bulk_wait_group_read0();  // the previous row's bulk stores have read the scratch vector
         __syncwarp();
+        float* st = nullptr;
+        if constexpr (kExt) {
+        if (p.stash) st = p.stash + ((size_t)blockIdx.x * kCholWarps + cw) * (size_t)(WP::kFloats + KS);
+        const float* ga = nullptr;
         if (acc >= 0) {
           // a chunk of a split row: add my partial -D and rhs to the row's record; whoever arrives last
           // assembles N = -(G + lambda alpha n_u I) + sum of the partials and solves
-          float* ga = p.gacc + (size_t)acc * (size_t)(WP::kFloats + KS);
-          for (int e = lane; e < WP::kFloats; e += 32) atomicAdd(ga + e, slot[e]);
+          float* gw = p.gacc + (size_t)acc * (size_t)(WP::kFloats + KS);
+          for (int e = lane; e < WP::kFloats; e += 32) atomicAdd(gw + e, slot[e]);
 #pragma unroll
-          for (int s = 0; s < CB::kS; s++) atomicAdd(ga + WP::kFloats + lane + 32 * s, b[s]);
+          for (int s = 0; s < CB::kS; s++) atomicAdd(gw + WP::kFloats + lane + 32 * s, b[s]);
           __threadfence();
           __syncwarp();
           int arrived = 0;
@@ -1038,14 +1052,28 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
             continue;
           }
           __threadfence();
-          const float lam_n = (float)(p.lambda_alpha * (double)(p.real_ptr[row + 1] - p.real_ptr[row]));
-          for (int e = lane; e < WP::kFloats; e += 32) slot[e] = ng[e] + __ldcg(ga + e);
-          __syncwarp();
-          for (int i = lane; i < KS; i += 32) slot[WP::at(i, i)] -= (i < k) ? lam_n : 1.f;
+          ga = gw;
 #pragma unroll
           for (int s = 0; s < CB::kS; s++) b[s] = __ldcg(ga + WP::kFloats + lane + 32 * s);
+        }
+        if (ga || st) {
+          // the slot holds -D only (chunks, stash mode) or nothing yet (assembled row): N = -G - D - lambda alpha n_u I,
+          // keeping a copy of -D and the rhs in stash mode
+          const float lam_n = (float)(p.lambda_alpha * (double)(p.real_ptr[row + 1] - p.real_ptr[row]));
+          for (int e = lane; e < WP::kFloats; e += 32) {
+            const float d = ga ? __ldcg(ga + e) : slot[e];
+            if (st) st[e] = d;
+            slot[e] = ng[e] + d;
+          }
+          if (st) {
+#pragma unroll
+            for (int s = 0; s < CB::kS; s++) st[WP::kFloats + lane + 32 * s] = b[s];
+          }
+          __syncwarp();
+          for (int i = lane; i < KS; i += 32) slot[WP::at(i, i)] -= (i < k) ? lam_n : 1.f;
           __syncwarp();
         }
+        }  // kExt
         const float dmax = CB::diag_max(slot, lane, k);
         const bool ok = CB::factor_solve(slot, scratch, b, dmax, p.threshold, kCondLimit, lane, k);
 #ifdef ALS_PROFILE_WAITS
@@ -1068,9 +1096,25 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
             for (int r = 0; r < p.n_peers; r++) bulk_s2g(p.peer_out[r] + eoff, smem_u32(xs), KS * 4);
             bulk_commit_group();  // (the scratch vector is reused only after wait_group.read, below)
           }
-        } else if (lane == 0) {
-          const int rs = atomicAdd(p.retry_count, 1);
-          p.retry_rows[rs] = (int)row;
+        } else {
+          // refused by the fp32 path.  Stash mode: my copy of -D and the rhs goes to the fp64 re-solve;
+          // otherwise (or when its buffer is full) the row is gathered again by the fp64 kernel.
+          bool handed = false;
+          if (kExt && st) {
+            int rs = 0;
+            if (lane == 0) rs = atomicAdd(p.resolve_count, 1);
+            rs = __shfl_sync(kFull, rs, 0);
+            if (rs < p.resolve_cap) {
+              float* rec = p.resolve_buf + (size_t)rs * (size_t)(WP::kFloats + KS);
+              for (int e = lane; e < WP::kFloats + KS; e += 32) rec[e] = st[e];  // (each lane re-reads what it wrote)
+              if (lane == 0) p.resolve_rows[rs] = (int)row;
+              handed = true;
+            }
+          }
+          if (!handed && lane == 0) {
+            const int rs = atomicAdd(p.retry_count, 1);
+            p.retry_rows[rs] = (int)row;
+          }
         }
         useq++;
       }
@@ -1092,13 +1136,13 @@ __global__ void __launch_bounds__(MX::kThreads, 1) row_update_v2_kernel(const Ro
 
 }  // namespace v2
 
-template <int KS, class MX>
+template <int KS, class MX, bool kExt = false>
 inline int launch_row_update_v2_t(const RowUpdateParams& p, const CUtensorMap& tmapM, int sm_count, cudaStream_t stream,
                                   char* err, size_t err_len) {
   using S = v2::Smem<KS, MX>;
   long long grid = sm_count;
   if (grid > p.n_rows) grid = p.n_rows > 0 ? p.n_rows : 1;
-  v2::row_update_v2_kernel<KS, MX><<<(int)grid, MX::kThreads, S::kTotal, stream>>>(p, tmapM);
+  v2::row_update_v2_kernel<KS, MX, kExt><<<(int)grid, MX::kThreads, S::kTotal, stream>>>(p, tmapM);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, err_len, "row_update_v2 launch: %s", cudaGetErrorString(e));

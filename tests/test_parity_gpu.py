@@ -258,6 +258,79 @@ def test_long_rows_split_into_chunks(M, O, monkeypatch, limit, k):
         assert fro <= TOL and mx <= TOL, (limit, k, fro, mx)
 
 
+def _ill_conditioned_problem(k):
+    """Ragged user rows against item vectors with a strong common component: for ~85 % of the user rows
+    max diagonal / min pivot of W_u is 300..1000 (numpy), past the fp32 solve's conditioning gate of 256."""
+    rng = np.random.default_rng(31 + k)
+    n_users, n_items = 2500, 1200
+    lens = np.concatenate([[1, 2, 17, 129, 257, 600],
+                           np.minimum(600, (rng.pareto(1.3, n_users - 6) * 10 + 2).astype(int))])
+    ptr, idx, val = [0], [], []
+    for n in lens:
+        idx += list(np.sort(rng.choice(n_items, size=n, replace=False)))
+        v = rng.integers(1, 6, size=n).astype(np.float32)
+        v[rng.random(n) < 0.05] *= -1
+        val += list(v)
+        ptr.append(len(idx))
+    ptr, idx, val = np.array(ptr, np.int64), np.array(idx, np.int32), np.array(val, np.float32)
+    d = 0.03 * rng.standard_normal((n_items, k))
+    d[:, 0] += 1.0   # (along one axis, so that the largest DIAGONAL entry -- what the gate looks at -- is ~n_items)
+    Y0 = (d / np.sqrt((d * d).sum(1))[:, None]).astype(np.float32)
+    return n_users, n_items, ptr, idx, val, Y0
+
+
+@pytest.mark.parametrize("k", [64, 32, 50])
+def test_stash_mode_resolves_rows_against_an_ill_conditioned_gramian(M, O, monkeypatch, k):
+    """Stash mode forced from the first launch: the tensor-core kernel hands the data term of the rows its
+    fp32 solve refuses to the fp64 re-solve (fp64 Gramian + tensor-core D, no second gather) instead of
+    the CUDA-core fp64 kernel.  Rows of more than 128 entries are split here, so rows assembled from chunks
+    take the path too.  Three iterations against the oracle."""
+    monkeypatch.setenv("MYRRIX_ALS_STASH", "1")
+    monkeypatch.setenv("MYRRIX_ALS_SPLIT_ROWS", "128")
+    n_users, n_items, ptr, idx, val, Y0 = _ill_conditioned_problem(k)
+    iters = 3
+    Xo, Yo, _, _ = O.als_run(ptr, idx, val, n_items, Y0, max_iterations=iters,
+                             convergence_threshold=1e-12, n_threads=8)
+    with M.NativeALS(k, kernel=2) as als:
+        als.set_interactions(n_users, n_items, ptr, idx, val)
+        als.set_y(Y0)
+        als.timings(reset=True)
+        als.iterate(iters)
+        als.sync()
+        X, Y = als.get_x(), als.get_y()
+        tm = als.timings()
+    assert tm.fp64_resolve_rows > n_users // 2, tm.fp64_resolve_rows   # the gate did refuse them
+    assert tm.fp64_retry_rows == tm.fp64_resolve_rows                   # and none was gathered again
+    for a, b in ((X, Xo), (Y, Yo)):
+        fro, mx = rel_err(a, b)
+        assert fro <= TOL and mx <= TOL, (k, fro, mx)
+
+
+def test_stash_mode_switches_on_after_a_launch_that_refused_many_rows(M, O, monkeypatch):
+    """Default policy: the first X-half sends the refused rows to the CUDA-core fp64 kernel and reports how
+    many there were; the next X-half (same Y, so the same rows fail) runs in stash mode.  Same result."""
+    monkeypatch.delenv("MYRRIX_ALS_STASH", raising=False)
+    k = 64
+    n_users, n_items, ptr, idx, val, Y0 = _ill_conditioned_problem(k)
+    out = np.zeros((n_users, k), np.float32)
+    O.als_half(ptr, idx, val, Y0, O.transpose_times_self(Y0), out, n_threads=8)
+    with M.NativeALS(k, kernel=2) as als:
+        als.set_interactions(n_users, n_items, ptr, idx, val)
+        als.set_y(Y0)
+        als.timings(reset=True)
+        als.half_x(); als.sync()
+        X1 = als.get_x()
+        t1 = als.timings(reset=True)
+        als.half_x(); als.sync()
+        X2 = als.get_x()
+        t2 = als.timings(reset=True)
+    assert t1.fp64_retry_rows > n_users // 2 and t1.fp64_resolve_rows == 0
+    assert t2.fp64_resolve_rows > n_users // 2 and t2.fp64_retry_rows == t2.fp64_resolve_rows
+    for X in (X1, X2):
+        fro, mx = rel_err(X, out)
+        assert fro <= TOL and mx <= TOL, (fro, mx)
+
+
 def test_csv_files_to_factors(M, O):
     """The step in front of the path joined to it: CSV lines with duplicates,
     deletions, near-zero sums and comments -> libmyrrix_ingest.so -> als_set_interactions ->
