@@ -183,6 +183,11 @@ def reference_arm(args, cfg, name):
     """--impl reference: no GPU code on this path. Workload rows from the numpy twin of the
     device generator (oracle/synth.py)."""
     from oracle import synth
+    if cfg.get("powerlaw"):
+        # (the item-row sampler below walks the uniform generator's strata; the power-law configs are bench
+        # lines of this repo only -- their CPU check is the sampled-row parity inside the b200 arm)
+        print(json.dumps({"impl": "reference", "unavailable": "no CPU arm for the power-law configs (c5p, c5)"}))
+        return
     U, I, nnz, k = cfg["users"], cfg["items"], cfg["nnz_per_user"], cfg["k"]
     nu, ni = sample_sizes(cfg)
     user_rows = synth.synth_rows(0, nu, I, nnz, seed=SEED, neg_fraction=0.0)
