@@ -148,3 +148,50 @@ def test_present_but_empty_rows_in_the_oracle_match_a_dense_solve():
     # without the masks the rows keep their previous contents (absent from the map)
     X2, Y2, _, _ = O.als_run(ptr, idx, val, I, Y0, max_iterations=3, convergence_threshold=1e-12)
     assert np.array_equal(Y2[I - 2], Y0[I - 2])
+
+
+def _ldlt_min_pivot(W):
+    """Unpivoted right-looking LDL^T in fp64: the pivots csrc/solve_fp64.cuh judges (pivot <= threshold -> singular)."""
+    W = W.copy()
+    m = np.inf
+    for j in range(W.shape[0]):
+        d = W[j, j]
+        m = min(m, d)
+        if not d > 0:
+            return d
+        l = W[j + 1:, j] / d
+        W[j + 1:, j + 1:] -= np.outer(l, W[j + 1:, j])
+    return m
+
+
+def test_where_the_ldlt_pivot_rule_and_the_rrqr_rule_part_ways():
+    """The reference declares W singular when a diagonal entry of the pivoted QR has |R_jj| <= 1e-5
+    (CommonsMathLinearSystemSolver.java:43-54); the CUDA fp64 path judges the LDL^T pivots against the same
+    threshold.  For SPD matrices with one small eigenvalue both rules agree when lambda_min >= 1e-5 (solved)
+    and when lambda_min <= 1e-13 (singular); in between the unpivoted pivot (~lambda_min / q^2, q the small
+    eigenvector's last-eliminated component) overestimates lambda_min by more than the pivoted |R_kk| does, so
+    the CUDA path still solves some systems the reference gives up on (known gaps).  Not reachable
+    with lambda > 0: lambda_min(W_u) >= lambda alpha n_u."""
+    rng = np.random.default_rng(0)
+    between = 0
+    for k in (8, 32, 64):
+        for lam_min in (1e-14, 1e-13, 1e-10, 1e-8, 1e-7, 1e-6, 1e-5, 2e-5, 1e-4):
+            for _ in range(8):
+                Q, _r = np.linalg.qr(rng.standard_normal((k, k)))
+                ev = rng.uniform(0.5, 2.0, k)
+                ev[rng.integers(k)] = lam_min
+                W = (Q * ev) @ Q.T
+                W = (W + W.T) / 2
+                try:
+                    O.solve(W, np.ones(k))
+                    rrqr_singular = False
+                except O.SingularMatrixError:
+                    rrqr_singular = True
+                ldlt_singular = not (_ldlt_min_pivot(W) > 1e-5)
+                if lam_min >= 1e-5:
+                    assert not rrqr_singular and not ldlt_singular, (k, lam_min)
+                elif lam_min <= 1e-13:
+                    assert rrqr_singular and ldlt_singular, (k, lam_min)
+                else:
+                    between += rrqr_singular != ldlt_singular
+    assert between > 0   # the band is real: keep DESIGN.md honest about it
