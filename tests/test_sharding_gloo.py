@@ -125,3 +125,52 @@ def test_block_layout_helpers():
     val = np.arange(6, dtype=np.float32)
     p, i, v = S.shard_rows(ptr, idx, val, 1, 2)
     assert list(p) == [0, 3, 4] and list(i) == [2, 3, 4, 5]
+
+
+def _powerlaw_worker(rank, world, port, out_dir):
+    """What als_synth_interactions_powerlaw does on a sharded handle (csrc/als_abi.cu), on CPU: every rank
+    draws its own user block from the counter-based generator, sorts its entries by item (stable: users stay
+    ascending), sends each item block's run to its owner, and merges what it receives -- ordered by source
+    rank, i.e. by user range -- with one more stable sort on the item (build_by_item_distributed)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import synth
+    from myrrix_recommender_b200 import sharding as S
+    U, I = 1501, 233
+    ub, ue = S.local_block(U, rank, world)
+    ib, ie = S.local_block(I, rank, world)
+    bi = S.block_rows(I, world)
+    ptr, idx, val = synth.synth_rows_powerlaw(ub, ue - ub, I, 20, max_nnz=150, seed=5, neg_fraction=0.1)
+    users = np.repeat(np.arange(ub, ue, dtype=np.int64), np.diff(ptr))
+    order = np.argsort(idx, kind="stable")
+    k_sorted, u_sorted, v_sorted = idx[order].astype(np.int64), users[order], val[order]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [(k_sorted[(k_sorted // bi) == r], u_sorted[(k_sorted // bi) == r],
+                                       v_sorted[(k_sorted // bi) == r]) for r in range(world)])
+    keys = np.concatenate([gathered[src][rank][0] for src in range(world)])
+    usr = np.concatenate([gathered[src][rank][1] for src in range(world)])
+    vals = np.concatenate([gathered[src][rank][2] for src in range(world)])
+    order = np.argsort(keys, kind="stable")
+    keys, usr, vals = keys[order] - ib, usr[order], vals[order]
+    cptr = np.zeros(ie - ib + 1, np.int64)
+    np.cumsum(np.bincount(keys, minlength=ie - ib), out=cptr[1:])
+    np.savez(os.path.join(out_dir, "pl%d.npz" % rank), ptr=ptr, idx=idx, val=val, cptr=cptr,
+             cidx=usr.astype(np.int32), cval=vals)
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_powerlaw_generation_and_by_item_exchange(tmp_path):
+    world = 2
+    mp.spawn(_powerlaw_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    from oracle import oracle as O, synth
+    from myrrix_recommender_b200 import sharding as S
+    U, I = 1501, 233
+    ptr, idx, val = synth.synth_rows_powerlaw(0, U, I, 20, max_nnz=150, seed=5, neg_fraction=0.1)
+    tp, ti, tv = O.csr_transpose(ptr, idx, val, I)
+    for r in range(world):
+        z = np.load(tmp_path / ("pl%d.npz" % r))
+        ep, ei, ev = S.shard_rows(ptr, idx, val, r, world)
+        assert np.array_equal(z["ptr"], ep) and np.array_equal(z["idx"], ei) and np.array_equal(z["val"], ev)
+        ep, ei, ev = S.shard_rows(tp, ti, tv, r, world)
+        assert np.array_equal(z["cptr"], ep) and np.array_equal(z["cidx"], ei) and np.array_equal(z["cval"], ev)
